@@ -1,0 +1,73 @@
+"""Pins the CPU restatement (oracle/) to the unmodified reference binary's outputs (tests/golden/)."""
+import os
+import tempfile
+
+import pytest
+
+from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
+from oracle import oracle as O
+from raft_b200 import synth
+
+CASES = manifest()
+
+
+@pytest.mark.parametrize("entry", CASES, ids=[e["name"] for e in CASES])
+def test_oracle_matches_reference_golden(entry):
+    fa, paf = load_inputs(entry)
+    reads = O.parse_fasta(fa)
+    res = O.run(reads, paf, O.make_params(**args_to_kw(entry["args"])))
+    assert res.status == 0
+    for suf, data in zip(SUFS, (res.cov_txt, res.rep_txt, res.bed_txt, res.fasta)):
+        check_output(entry, suf, data)
+    assert stdout_value(entry, "Symmetric overlaps") == f"INFO, Symmetric overlaps {res.symmetric} "
+    assert stdout_value(entry, "length of alignments") == f"INFO, length of alignments  {res.n_rec}()"
+    assert stdout_value(entry, "high_cov") == f"high_cov {res.high_cov}"
+    assert stdout_value(entry, "Real Reads") == f"Real Reads {res.real_reads} "
+    cpw = res.total_cov / res.total_windows if res.total_windows else float("nan")
+    assert stdout_value(entry, "coverage per window is") == "coverage per window is %f " % cpw
+    assert stdout_value(entry, "fraction_of_repeat_length") == "fraction_of_repeat_length %f " % (
+        res.total_repeat_len / res.total_read_len)
+
+
+def test_oracle_defined_domain_errors():
+    fa = b">a\nACGTACGTAC\n>b\nACGTACGTACGG\n"
+    reads = O.parse_fasta(fa)
+    line = lambda *f: b"\t".join(str(x).encode() for x in f) + b"\n"
+    ok = line("a", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255)
+    assert O.run(reads, ok, O.make_params(est_cov=1)).status == 0
+    # unknown name: the reference indexes out of range (chop.hpp:162-168)
+    assert O.run(reads, line("zz", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255), O.make_params(est_cov=1)).status == -2
+    # interval past the last bin: the reference writes out of bounds (repeat.hpp:69-73)
+    assert O.run(reads, line("a", 10, 0, 500, "+", "b", 12, 0, 10, 10, 10, 255), O.make_params(est_cov=1)).status == -4
+    # l < p: div = 0 -> SIGFPE in the reference (chop.hpp:248,270)
+    assert O.run(reads, ok, O.make_params(est_cov=1, read_length=50, repeat_length=100)).status == -1
+    # duplicate FASTA names alias ids in the reference (chop.hpp:73-85)
+    assert O.run(O.parse_fasta(b">a\nAC\n>a\nGT\n"), b"", O.make_params(est_cov=1)).status == -3
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/raft not built (reference sources not mounted)")
+@pytest.mark.parametrize("cfg,scale,sym", [("C1", 0.05, True), ("C1", 0.05, False), ("C5", 0.001, False),
+                                           ("C4", 0.0004, True), ("C2", 0.00006, False)])
+def test_oracle_matches_reference_binary_live(cfg, scale, sym):
+    ds = synth.make_dataset(cfg, scale, sym, seed=1234)
+    with tempfile.TemporaryDirectory() as d:
+        fa, pf = os.path.join(d, "r.fa"), os.path.join(d, "o.paf")
+        fa_bytes = synth.format_fasta(ds.reads, wrap=61)
+        open(fa, "wb").write(fa_bytes)
+        open(pf, "wb").write(ds.paf)
+        rc, out, files = O.run_ref(fa, pf, d, ds.args)
+    assert rc == 0, out
+    reads = O.parse_fasta(fa_bytes)
+    assert (reads.seq_off == ds.reads.seq_off).all() and (reads.seq == ds.reads.seq).all()
+    assert (reads.names == ds.reads.names).all()
+    res = O.run(reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    assert res.status == 0
+    for suf, data in zip(SUFS, (res.cov_txt, res.rep_txt, res.bed_txt, res.fasta)):
+        assert files.get(suf, b"") == data, suf
+
+
+def test_digest_is_window_additive():
+    data = bytes(range(256)) * 7
+    whole = O.digest(data)
+    parts = (O.digest(data[:100], 0) + O.digest(data[100:1000], 100) + O.digest(data[1000:], 1000)) & (2**64 - 1)
+    assert whole == parts
