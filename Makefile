@@ -1,0 +1,34 @@
+# Builds the B200-native library, the `raft` CLI on top of it, and the test oracle.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
+SRC       := raft_b200/csrc
+OBJ       := build
+CU        := nametable k1_paf k2_coverage k3_repeat_cut k5_emit api
+OBJS      := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/host_io.o
+LIB       := raft_b200/libraft_b200.so
+
+all: $(LIB) raft_b200/raft oracle
+
+$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh include/raft_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/host_io.o: $(SRC)/host_io.cpp include/raft_b200.h
+	@mkdir -p $(OBJ)
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz
+
+raft_b200/raft: $(SRC)/raft_main.cpp $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -Lraft_b200 -lraft_b200 -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf $(OBJ) $(LIB) raft_b200/raft
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean

@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's interface for the fragmentation path, on top of the C ABI.
+
+Reference seam (SURVEY.md §8 row b): `break_long_reads(reads, paf, unused, algoParams&)` (chop.hpp:331)
+and its stages loadFASTA / create_pileup / repeat_annotate / break_reads.  Names and argument meaning
+follow the reference; errors the reference reports by exit(1) or by crashing surface as RaftError.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+OUT_COVERAGE, OUT_LONG_REPEATS, OUT_BED, OUT_READS_FASTA = 0, 1, 2, 3
+OUT_SUFFIX = {OUT_COVERAGE: "coverage.txt", OUT_LONG_REPEATS: "long_repeats.txt", OUT_BED: "long_repeats.bed",
+              OUT_READS_FASTA: "reads.fasta"}
+(TAB_QID, TAB_TID, TAB_QS, TAB_QE, TAB_TS, TAB_TE, TAB_STRAND, TAB_BIN_OFF, TAB_COV, TAB_REP_OFF, TAB_REP,
+ TAB_FRAG) = range(12)
+_TAB_DTYPE = {TAB_STRAND: np.uint8, TAB_BIN_OFF: np.int64, TAB_REP_OFF: np.int64}
+
+
+class RaftError(RuntimeError):
+    def __init__(self, status, detail="", index=-1):
+        self.status, self.index = status, index
+        msg = _lib.lib().raftgpu_strerror(status).decode()
+        super().__init__(f"[{status}] {msg}" + (f": {detail}" if detail else ""))
+
+
+@dataclass
+class AlgoParams:
+    """algoParams (param.hpp:4-31).  -p sets both repeat_length and interval_length (main.cpp:44-47)."""
+    reso: int = 50
+    est_cov: int = 0
+    cov_mul: float = 1.5
+    repeat_length: int = 10000
+    interval_length: int = None
+    read_length: int = 20000
+    overlap_length: int = 500
+    flanking_length: int = 1000
+    outputfilename: str = "raft"
+
+    def c_struct(self):
+        il = self.repeat_length if self.interval_length is None else self.interval_length
+        return _lib.Params(self.reso, self.est_cov, self.cov_mul, self.repeat_length, il, self.read_length,
+                           self.overlap_length, self.flanking_length)
+
+    @classmethod
+    def from_args(cls, args):
+        """Parse reference CLI flags (main.cpp:28-59), including the -v -> -o fallthrough."""
+        p = cls()
+        it = iter(args)
+        for flag in it:
+            val = next(it)
+            if flag == "-r": p.reso = int(val)
+            elif flag == "-e": p.est_cov = int(val)
+            elif flag == "-m": p.cov_mul = float(val)
+            elif flag == "-l": p.read_length = int(val)
+            elif flag == "-p": p.repeat_length = int(val); p.interval_length = int(val)
+            elif flag == "-f": p.flanking_length = int(val)
+            elif flag == "-v": p.overlap_length = int(val); p.outputfilename = val
+            elif flag == "-o": p.outputfilename = val
+            else: raise ValueError(flag)
+        return p
+
+
+def _ptr(a):
+    """Host numpy array / bytes / torch tensor (host or CUDA) / int address -> void* value."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data if a.size else None
+    if isinstance(a, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(a)), C.c_void_p).value if len(a) else None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class Context:
+    """One GPU's state for the path (raftgpu_ctx)."""
+
+    def __init__(self, params: AlgoParams, device: int = 0):
+        self.L = _lib.lib()
+        self.params = params
+        self._h = C.c_void_p()
+        self._keep = []
+        st = self.L.raftgpu_create(C.byref(params.c_struct()), device, C.byref(self._h))
+        if st:
+            raise RaftError(st, "raftgpu_create (is there a B200? the library has no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            self.L.raftgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st:
+            raise RaftError(st, self.L.raftgpu_last_error(self._h).decode(), self.L.raftgpu_error_index(self._h))
+
+    # ---- a0 loadFASTA (chop.hpp:88-131), after tokenisation
+    def set_reads(self, seq_off, seq, name_off, names):
+        self._keep = [seq_off, seq, name_off, names]
+        n = len(seq_off) - 1
+        self._ck(self.L.raftgpu_set_reads(self._h, n, _ptr(seq_off), _ptr(seq), _ptr(name_off), _ptr(names)))
+
+    def set_reads_sharded(self, n, lengths, name_off, names, own_first, own_count, own_seq_off, own_seq):
+        self._keep = [lengths, name_off, names, own_seq_off, own_seq]
+        self._ck(self.L.raftgpu_set_reads_sharded(self._h, n, _ptr(lengths), _ptr(name_off), _ptr(names), own_first,
+                                                  own_count, _ptr(own_seq_off), _ptr(own_seq)))
+
+    # ---- a1/a2 create_pileup (chop.hpp:133-191)
+    def ingest_paf(self, text, nbytes=None, last=True):
+        if nbytes is None:
+            nbytes = len(text) if not hasattr(text, "numel") else text.numel()
+        self._keep.append(text)
+        self._ck(self.L.raftgpu_ingest_paf(self._h, _ptr(text), nbytes, 1 if last else 0))
+
+    # ---- a3-a5 repeat_annotate + break_reads arithmetic
+    def run(self):
+        s = _lib.Stats()
+        self._ck(self.L.raftgpu_run(self._h, C.byref(s)))
+        return s
+
+    def finalize(self):
+        s = _lib.Stats()
+        self._ck(self.L.raftgpu_finalize(self._h, C.byref(s)))
+        return s
+
+    def output_size(self, which):
+        n = C.c_uint64()
+        self._ck(self.L.raftgpu_output_size(self._h, which, C.byref(n)))
+        return n.value
+
+    def fetch(self, which, off=0, n=None) -> bytes:
+        if n is None:
+            n = self.output_size(which) - off
+        buf = np.empty(max(n, 1), dtype=np.uint8)
+        self._ck(self.L.raftgpu_fetch(self._h, which, off, buf.ctypes.data, n))
+        return buf[:n].tobytes()
+
+    def fetch_into(self, which, off, dst, n):
+        self._ck(self.L.raftgpu_fetch(self._h, which, off, _ptr(dst), n))
+
+    def digest(self, which) -> int:
+        d = C.c_uint64()
+        self._ck(self.L.raftgpu_digest(self._h, which, C.byref(d)))
+        return d.value
+
+    def table(self, tab) -> np.ndarray:
+        n = C.c_size_t()
+        self._ck(self.L.raftgpu_fetch_table(self._h, tab, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=_TAB_DTYPE.get(tab, np.int32))
+        if n.value:
+            self._ck(self.L.raftgpu_fetch_table(self._h, tab, out.ctypes.data, out.nbytes, C.byref(n)))
+        return out
+
+    # ---- multi-GPU plumbing
+    def peek_first_record(self, text, nbytes):
+        rec, found = (C.c_int32 * 6)(), C.c_int32()
+        self._ck(self.L.raftgpu_peek_first_record(self._h, _ptr(text), nbytes, C.byref(rec), C.byref(found)))
+        return list(rec), bool(found.value)
+
+    def set_first_record(self, rec, is_local):
+        arr = (C.c_int32 * 6)(*rec) if rec is not None else None
+        self._ck(self.L.raftgpu_set_first_record(self._h, C.byref(arr) if arr is not None else None, 1 if is_local else 0))
+
+    def get_symmetric(self):
+        f = C.c_int32()
+        self._ck(self.L.raftgpu_get_symmetric(self._h, C.byref(f)))
+        return int(f.value)
+
+    def set_symmetric(self, flag):
+        self._ck(self.L.raftgpu_set_symmetric(self._h, int(flag)))
+
+    def route_count(self, bounds: np.ndarray) -> np.ndarray:
+        nr = len(bounds) - 1
+        counts = np.zeros(nr, dtype=np.int64)
+        self._ck(self.L.raftgpu_route_count(self._h, nr, bounds.ctypes.data, counts.ctypes.data))
+        return counts
+
+    def route_pack(self, bounds: np.ndarray, counts: np.ndarray, sendbuf):
+        self._ck(self.L.raftgpu_route_pack(self._h, len(counts), bounds.ctypes.data, counts.ctypes.data, _ptr(sendbuf)))
+
+    def accumulate_endpoints(self, ep, count):
+        self._ck(self.L.raftgpu_accumulate_endpoints(self._h, _ptr(ep), count))
+
+    def set_output_base(self, first_read_num):
+        self._ck(self.L.raftgpu_set_output_base(self._h, first_read_num))
+
+
+def load_fasta(path):
+    """loadFASTA's record reader (chop.hpp:88-131 / kseq.h:240-298) -> (seq_off, seq, name_off, names)."""
+    L = _lib.lib()
+    n = C.c_int64()
+    so, sq, no, nm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    st = L.raftgpu_load_fasta(path.encode(), C.byref(n), C.byref(so), C.byref(sq), C.byref(no), C.byref(nm))
+    if st:
+        raise RaftError(st, path)
+    try:
+        seq_off = np.ctypeslib.as_array(C.cast(so, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+        name_off = np.ctypeslib.as_array(C.cast(no, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+        ns, nn = int(seq_off[-1]), int(name_off[-1])
+        seq = np.ctypeslib.as_array(C.cast(sq, C.POINTER(C.c_uint8)), shape=(max(ns, 1),))[:ns].copy()
+        names = np.ctypeslib.as_array(C.cast(nm, C.POINTER(C.c_uint8)), shape=(max(nn, 1),))[:nn].copy()
+    finally:
+        for p in (so, sq, no, nm):
+            L.raftgpu_free_host(p)
+    return seq_off, seq, name_off, names
+
+
+def break_long_reads(readfilename: str, paffilename: str, params: AlgoParams, device: int = 0):
+    """Drop-in for break_long_reads (chop.hpp:331-373): files in, prefix.* files out."""
+    L = _lib.lib()
+    s = _lib.Stats()
+    st = L.raftgpu_break_long_reads(readfilename.encode(), paffilename.encode(), C.byref(params.c_struct()),
+                                    params.outputfilename.encode(), device, C.byref(s))
+    if st:
+        raise RaftError(st)
+    return s

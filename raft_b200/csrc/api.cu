@@ -1,0 +1,925 @@
+// api.cu — context, stage sequencing and the extern "C" boundary of libraft_b200.so
+// (declared in include/raft_b200.h).  Host logic only; all compute is in the k*.cu kernels.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/raft_b200.h"
+#include "kernels.h"
+
+using namespace raftk;
+
+namespace {
+
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // grow to at least `bytes` (contents NOT preserved unless keep > 0 bytes)
+    cudaError_t ensure(size_t bytes, size_t keep = 0, cudaStream_t st = 0)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 8 + 256;
+        void*  np = nullptr;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&np, bytes + 256); want = bytes + 256; }
+        if (e != cudaSuccess) return e;
+        if (keep && p) { e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// misc device scalars
+struct Misc {
+    int                rec0[8];
+    int                sym_flag;
+    int                ticket;
+    int                work_counter;
+    int                pad;
+    ErrState           err;
+    long long          n_records_out;
+    unsigned long long stats[2];
+    unsigned long long digest;
+    unsigned long long route_counts[64];
+};
+
+constexpr size_t WINDOW_BYTES = 256ull << 20; // staging window for host fetches
+
+} // namespace
+
+struct raftgpu_ctx {
+    int            device = 0;
+    cudaStream_t   st = nullptr, st2 = nullptr;
+    raftgpu_params prm{};
+    std::string    last_error;
+    int64_t        err_index = -1;
+    int            launches = 0;
+
+    // reads
+    bool    have_reads = false, have_seq = false;
+    int64_t n = 0, own_first = 0, m = 0;
+    int     real_reads = 1;
+    const int64_t* d_name_off = nullptr; const uint8_t* d_names = nullptr;
+    const int64_t* d_seq_off = nullptr;  const uint8_t* d_seq = nullptr;
+    DevBuf  b_name_off, b_names, b_seq_off, b_seq;
+    DevBuf  b_slots, b_repcap, b_cutcap, b_slot_off, b_rep_cap_off, b_cut_cap_off;
+    int64_t n_slots = 0, rep_cap_total = 0, cut_cap_total = 0, total_read_len = 0;
+    DevBuf  b_table; NameTable nt{};
+
+    // records
+    DevBuf  b_qid, b_tid, b_qs, b_qe, b_ts, b_te, b_strand;
+    int64_t rec_cap = 0, n_rec = 0;
+    DevBuf  b_text;
+    std::vector<uint8_t> carry;
+    bool    first_is_local = true, rec0_external = false, sym_external = false, paf_done = false;
+    int64_t paf_bytes = 0;
+
+    DevBuf  b_misc, b_status;
+    Misc*   misc() const { return b_misc.as<Misc>(); }
+
+    // coverage + K3 + layout
+    DevBuf  b_cov; bool diff_zeroed = false, finalized = false, sized = false;
+    DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
+    DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
+    DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off;
+    std::vector<int64_t> h_cov_tile_off, h_rep_line_off;
+    int64_t G = 0, n_repeats = 0, read_num_base = 0;
+    raftgpu_stats stats{};
+    DevBuf  b_stage[2];
+    cudaEvent_t ev[8]{};
+    cudaEvent_t ev_stage[2]{};
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            cudaGetLastError();                                                                          \
+            return e_ == cudaErrorMemoryAllocation ? RAFTGPU_E_NOMEM : RAFTGPU_E_CUDA;                   \
+        }                                                                                                \
+    } while (0)
+#define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+#define FAIL(code, msg) do { ctx->last_error = (msg); return (code); } while (0)
+
+static int check_params(const raftgpu_params& p)
+{ // the reference divides by these (repeat.hpp:32, chop.hpp:209,248,270) or emits a repeat per bin (repeat.hpp:125 with p<1)
+    if (p.reso < 1 || p.repeat_length < 1 || p.interval_length < 1 || p.read_length < p.interval_length) return RAFTGPU_E_PARAM;
+    return RAFTGPU_OK;
+}
+
+// chop.hpp:99-106: ^read=[0-9]+,[a-z]+,position=[0-9]+-[0-9]+,length=[0-9]+,(.*)
+static bool is_simulated_name(const std::string& s)
+{
+    size_t i = 0;
+    auto lit = [&](const char* t) { size_t l = strlen(t); if (s.compare(i, l, t) != 0) return false; i += l; return true; };
+    auto plus = [&](char lo, char hi) { size_t j = i; while (i < s.size() && s[i] >= lo && s[i] <= hi) i++; return i > j; };
+    return lit("read=") && plus('0', '9') && lit(",") && plus('a', 'z') && lit(",position=") && plus('0', '9') && lit("-") &&
+           plus('0', '9') && lit(",length=") && plus('0', '9') && lit(",");
+}
+
+extern "C" {
+
+void raftgpu_default_params(raftgpu_params* p)
+{
+    p->reso = 50; p->est_cov = 0; p->cov_mul = 1.5; p->repeat_length = 10000; p->interval_length = 10000;
+    p->read_length = 20000; p->overlap_length = 500; p->flanking_length = 1000;
+}
+
+const char* raftgpu_strerror(int s)
+{
+    switch (s) {
+    case RAFTGPU_OK: return "ok";
+    case RAFTGPU_E_PARAM: return "invalid parameters (need reso>=1, repeat_length>=1, read_length>=interval_length>=1)";
+    case RAFTGPU_E_UNKNOWN_NAME: return "PAF names a read that is not in the reads file";
+    case RAFTGPU_E_DUP_NAME: return "duplicate read name";
+    case RAFTGPU_E_RANGE: return "overlap interval extends past the end of its read";
+    case RAFTGPU_E_NEG_START: return "overlap_length larger than a cut position (fragment would start before 0)";
+    case RAFTGPU_E_NOMEM: return "out of memory";
+    case RAFTGPU_E_FASTQ: return "truncated FASTQ record";
+    case RAFTGPU_E_CUDA: return "CUDA error (no usable sm_100 device?)";
+    case RAFTGPU_E_STATE: return "call order violated";
+    case RAFTGPU_E_IO: return "input file missing/empty or output not writable";
+    case RAFTGPU_E_ARG: return "bad argument";
+    case RAFTGPU_E_UNSUPPORTED: return "not supported";
+    default: return "unknown status";
+    }
+}
+const char* raftgpu_last_error(const raftgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int64_t     raftgpu_error_index(const raftgpu_ctx* ctx) { return ctx ? ctx->err_index : -1; }
+
+int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
+{
+    if (!p || !out) return RAFTGPU_E_ARG;
+    *out = nullptr;
+    int st = check_params(*p);
+    if (st) return st;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return RAFTGPU_E_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) return RAFTGPU_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return RAFTGPU_E_CUDA; // sm_100a code only
+    raftgpu_ctx* ctx = new raftgpu_ctx();
+    ctx->device = device; ctx->prm = *p;
+    auto bail = [&](void) { delete ctx; return RAFTGPU_E_CUDA; };
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
+    for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
+    if (ctx->b_misc.ensure(sizeof(Misc)) != cudaSuccess) return bail();
+    *out = ctx;
+    return raftgpu_reset(ctx);
+}
+
+int raftgpu_destroy(raftgpu_ctx* ctx)
+{
+    if (!ctx) return RAFTGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
+    delete ctx;
+    return RAFTGPU_OK;
+}
+
+int raftgpu_reset(raftgpu_ctx* ctx)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Misc h{};
+    h.err.index = LLONG_MAX;
+    CK(cudaMemcpyAsync(ctx->b_misc.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->have_reads = ctx->have_seq = false; ctx->n = ctx->m = ctx->own_first = 0;
+    ctx->n_rec = 0; ctx->carry.clear(); ctx->first_is_local = true; ctx->rec0_external = ctx->sym_external = false;
+    ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
+    ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
+    ctx->stats = raftgpu_stats{};
+    return RAFTGPU_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+static int fetch_err(raftgpu_ctx* ctx)
+{ // read the device error word (stream must be synchronised by the caller or here)
+    ErrState e;
+    CK(cudaMemcpyAsync(&e, &ctx->misc()->err, sizeof e, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (e.index != LLONG_MAX) {
+        ctx->err_index = e.index;
+        char buf[160];
+        snprintf(buf, sizeof buf, "%s (index %lld)", raftgpu_strerror(e.code), e.index);
+        ctx->last_error = buf;
+        return e.code;
+    }
+    return RAFTGPU_OK;
+}
+
+// copy `bytes` from src (host or device) into an owned device buffer, or borrow a device pointer
+template <typename T>
+static int adopt(raftgpu_ctx* ctx, DevBuf& buf, const T* src, size_t count, const T** out, size_t pad_bytes = 32)
+{
+    size_t bytes = count * sizeof(T);
+    if (src && is_device_ptr(src) && ((uintptr_t)src & 15) == 0) { *out = src; return RAFTGPU_OK; }
+    CK(buf.ensure(bytes + pad_bytes));
+    if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyDefault, ctx->st));
+    CK(cudaMemsetAsync((uint8_t*)buf.p + bytes, 0, pad_bytes, ctx->st));
+    *out = buf.as<T>();
+    return RAFTGPU_OK;
+}
+
+static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_name)
+{
+    const raftgpu_params& P = ctx->prm;
+    ctx->real_reads = is_simulated_name(first_name) ? 0 : 1; // chop.hpp:99-106 (first record only)
+    const int64_t m = ctx->m;
+    // per-read slot / capacity layout (three exclusive scans)
+    CK(ctx->b_slots.ensure(sizeof(int32_t) * (m + 1))); CK(ctx->b_repcap.ensure(sizeof(int32_t) * (m + 1)));
+    CK(ctx->b_cutcap.ensure(sizeof(int32_t) * (m + 1)));
+    CK(ctx->b_slot_off.ensure(sizeof(int64_t) * (m + 1))); CK(ctx->b_rep_cap_off.ensure(sizeof(int64_t) * (m + 1)));
+    CK(ctx->b_cut_cap_off.ensure(sizeof(int64_t) * (m + 1)));
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (scan_tiles_small(m) + 8)));
+    launch_read_layout(ctx->d_seq_off, m, P.reso, P.repeat_length, P.interval_length, P.read_length, ctx->b_slots.as<int32_t>(),
+                       ctx->b_repcap.as<int32_t>(), ctx->b_cutcap.as<int32_t>(), ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_slots.as<int32_t>(), ctx->b_slot_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_repcap.as<int32_t>(), ctx->b_rep_cap_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_cutcap.as<int32_t>(), ctx->b_cut_cap_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);
+    CKL();
+    int64_t tot[3], seq_total = 0;
+    CK(cudaMemcpyAsync(&tot[0], ctx->b_slot_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&tot[1], ctx->b_rep_cap_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&tot[2], ctx->b_cut_cap_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&seq_total, ctx->d_seq_off + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    // name table: capacity = next pow2 >= 2n, re-seeded on a 64-bit collision
+    unsigned long long cap = 16;
+    while (cap < 2ull * (unsigned long long)ctx->n) cap <<= 1;
+    CK(ctx->b_table.ensure(cap * sizeof(NameSlot)));
+    for (unsigned long long seed = 0x5EEDull;; seed = seed * 6364136223846793005ull + 1442695040888963407ull) {
+        CK(launch_name_build(&ctx->nt, ctx->b_table.p, cap, seed, ctx->d_names, ctx->d_name_off, ctx->n, &ctx->misc()->err, ctx->st));
+        ctx->launches += 3;
+        int st = fetch_err(ctx);
+        if (st == RAFTK_E_HASH_COLLISION) { // astronomically rare: rebuild with another seed
+            ErrState clean{LLONG_MAX, 0, 0};
+            CK(cudaMemcpyAsync(&ctx->misc()->err, &clean, sizeof clean, cudaMemcpyHostToDevice, ctx->st));
+            continue;
+        }
+        if (st) return st;
+        break;
+    }
+    ctx->n_slots = tot[0]; ctx->rep_cap_total = tot[1]; ctx->cut_cap_total = tot[2];
+    ctx->total_read_len = seq_total; // owned reads only (summed across ranks by the caller when sharded)
+    ctx->have_reads = true;
+    return RAFTGPU_OK;
+}
+
+static int first_name_of(raftgpu_ctx* ctx, int64_t n, const int64_t* name_off, const uint8_t* names, std::string& out)
+{
+    out.clear();
+    if (n <= 0) return RAFTGPU_OK;
+    int64_t o[2];
+    CK(cudaMemcpy(o, name_off, 16, cudaMemcpyDefault));
+    size_t len = (size_t)(o[1] - o[0]);
+    out.resize(len);
+    if (len) CK(cudaMemcpy(&out[0], names + o[0], len, cudaMemcpyDefault));
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_set_reads(raftgpu_ctx* ctx, int64_t n, const int64_t* seq_off, const uint8_t* seq, const int64_t* name_off,
+                                 const uint8_t* names)
+{
+    if (!ctx || n < 0 || !seq_off || !name_off || n > 0x7ffffff0ll) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int st = raftgpu_reset(ctx);
+    if (st) return st;
+    int64_t name_bytes = 0, seq_bytes = 0;
+    CK(cudaMemcpy(&name_bytes, name_off + n, 8, cudaMemcpyDefault));
+    CK(cudaMemcpy(&seq_bytes, seq_off + n, 8, cudaMemcpyDefault));
+    ctx->n = n; ctx->m = n; ctx->own_first = 0;
+    if ((st = adopt(ctx, ctx->b_name_off, name_off, (size_t)n + 1, &ctx->d_name_off))) return st;
+    if ((st = adopt(ctx, ctx->b_names, names, (size_t)name_bytes, &ctx->d_names))) return st;
+    if ((st = adopt(ctx, ctx->b_seq_off, seq_off, (size_t)n + 1, &ctx->d_seq_off))) return st;
+    ctx->have_seq = seq != nullptr || seq_bytes == 0;
+    if (seq) { if ((st = adopt(ctx, ctx->b_seq, seq, (size_t)seq_bytes, &ctx->d_seq))) return st; }
+    else ctx->d_seq = nullptr;
+    std::string first;
+    if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
+    return build_layout_and_names(ctx, first);
+}
+
+extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int64_t* lengths, const int64_t* name_off, const uint8_t* names,
+                                         int64_t own_first, int64_t own_count, const int64_t* own_seq_off, const uint8_t* own_seq)
+{
+    if (!ctx || n < 0 || !name_off || own_first < 0 || own_count < 0 || own_first + own_count > n || n > 0x7ffffff0ll) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int st = raftgpu_reset(ctx);
+    if (st) return st;
+    int64_t name_bytes = 0, seq_bytes = 0;
+    CK(cudaMemcpy(&name_bytes, name_off + n, 8, cudaMemcpyDefault));
+    ctx->n = n; ctx->m = own_count; ctx->own_first = own_first;
+    if ((st = adopt(ctx, ctx->b_name_off, name_off, (size_t)n + 1, &ctx->d_name_off))) return st;
+    if ((st = adopt(ctx, ctx->b_names, names, (size_t)name_bytes, &ctx->d_names))) return st;
+    if (own_seq_off) {
+        CK(cudaMemcpy(&seq_bytes, own_seq_off + own_count, 8, cudaMemcpyDefault));
+        if ((st = adopt(ctx, ctx->b_seq_off, own_seq_off, (size_t)own_count + 1, &ctx->d_seq_off))) return st;
+    } else {
+        // lengths only: build local offsets on the host from the global length array
+        if (!lengths) return RAFTGPU_E_ARG;
+        std::vector<int64_t> len(own_count), off(own_count + 1, 0);
+        if (own_count) CK(cudaMemcpy(len.data(), lengths + own_first, sizeof(int64_t) * own_count, cudaMemcpyDefault));
+        for (int64_t i = 0; i < own_count; i++) off[i + 1] = off[i] + len[i];
+        seq_bytes = off[own_count];
+        const int64_t* tmp = nullptr;
+        CK(ctx->b_seq_off.ensure(sizeof(int64_t) * (own_count + 1) + 32));
+        CK(cudaMemcpy(ctx->b_seq_off.p, off.data(), sizeof(int64_t) * (own_count + 1), cudaMemcpyHostToDevice));
+        (void)tmp;
+        ctx->d_seq_off = ctx->b_seq_off.as<int64_t>();
+    }
+    ctx->have_seq = own_seq != nullptr || seq_bytes == 0;
+    if (own_seq) { if ((st = adopt(ctx, ctx->b_seq, own_seq, (size_t)seq_bytes, &ctx->d_seq))) return st; }
+    else ctx->d_seq = nullptr;
+    std::string first;
+    if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
+    return build_layout_and_names(ctx, first);
+}
+
+// ------------------------------------------------------------------------------------------------ PAF
+static int ensure_records(raftgpu_ctx* ctx, int64_t cap)
+{
+    if (cap <= ctx->rec_cap) return RAFTGPU_OK;
+    cap += cap / 8 + 1024;
+    size_t keep4 = sizeof(int32_t) * (size_t)ctx->n_rec, keep1 = (size_t)ctx->n_rec;
+    CK(ctx->b_qid.ensure(sizeof(int32_t) * cap, keep4, ctx->st)); CK(ctx->b_tid.ensure(sizeof(int32_t) * cap, keep4, ctx->st));
+    CK(ctx->b_qs.ensure(sizeof(int32_t) * cap, keep4, ctx->st));  CK(ctx->b_qe.ensure(sizeof(int32_t) * cap, keep4, ctx->st));
+    CK(ctx->b_ts.ensure(sizeof(int32_t) * cap, keep4, ctx->st));  CK(ctx->b_te.ensure(sizeof(int32_t) * cap, keep4, ctx->st));
+    CK(ctx->b_strand.ensure((size_t)cap, keep1, ctx->st));
+    ctx->rec_cap = cap;
+    return RAFTGPU_OK;
+}
+
+// tokenise `len` bytes of device text (complete lines, except that the last line may lack its newline)
+static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
+{
+    if (len <= 0) return RAFTGPU_OK;
+    Misc* M = ctx->misc();
+    if (!ctx->rec0_external) { // first record of the file: peek until one is found (no-op kernel once present)
+        int present = 0;
+        CK(cudaMemcpyAsync(&present, &M->rec0[6], sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (!present) { launch_paf_peek(dtext, len, ctx->nt, M->rec0, &M->err, ctx->st); CKL(); }
+    }
+    const int tiles = paf_tokenize_tiles(len);
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(tiles + 8)));
+    int st = ensure_records(ctx, ctx->n_rec + len / 48 + 1024);
+    if (st) return st;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(cudaMemsetAsync(ctx->b_status.p, 0, sizeof(uint64_t) * (size_t)tiles, ctx->st));
+        CK(cudaMemsetAsync(&M->ticket, 0, sizeof(int), ctx->st));
+        PafTokArgs a{};
+        a.text = dtext; a.nbytes = len; a.rec_base = ctx->n_rec; a.rec_cap = ctx->rec_cap;
+        a.qid = ctx->b_qid.as<int32_t>(); a.tid = ctx->b_tid.as<int32_t>(); a.qs = ctx->b_qs.as<int32_t>(); a.qe = ctx->b_qe.as<int32_t>();
+        a.ts = ctx->b_ts.as<int32_t>(); a.te = ctx->b_te.as<int32_t>(); a.strand = ctx->b_strand.as<uint8_t>();
+        a.rec0 = M->rec0; a.first_is_local = ctx->first_is_local ? 1 : 0; a.n_tiles = tiles;
+        a.status = ctx->b_status.as<uint64_t>(); a.ticket = &M->ticket; a.sym_flag = &M->sym_flag; a.err = &M->err;
+        a.n_records_out = (int64_t*)&M->n_records_out; a.names = ctx->nt;
+        CK(launch_paf_tokenize(a, ctx->st));
+        ctx->launches++;
+        long long n_out = 0;
+        CK(cudaMemcpyAsync(&n_out, &M->n_records_out, sizeof n_out, cudaMemcpyDeviceToHost, ctx->st));
+        if ((st = fetch_err(ctx))) return st;
+        if (n_out > 0x7fffffffll) FAIL(RAFTGPU_E_ARG, "more than 2^31-1 PAF records (the reference counts them in an int, chop.hpp:139)");
+        if (n_out <= ctx->rec_cap) { ctx->n_rec = n_out; return RAFTGPU_OK; }
+        if ((st = ensure_records(ctx, n_out))) return st; // optimistic capacity was too small: grow and redo this chunk
+    }
+    FAIL(RAFTGPU_E_STATE, "record capacity retry failed");
+}
+
+extern "C" int raftgpu_ingest_paf(raftgpu_ctx* ctx, const uint8_t* text, size_t nbytes, int last_chunk)
+{
+    if (!ctx || (!text && nbytes)) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads || ctx->paf_done) FAIL(RAFTGPU_E_STATE, "raftgpu_ingest_paf: set reads first / PAF already complete");
+    CK(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev[0], ctx->st);
+    const bool dev = nbytes && is_device_ptr(text);
+    const size_t total = ctx->carry.size() + nbytes;
+    ctx->paf_bytes += (int64_t)nbytes;
+    const uint8_t* dtext = nullptr;
+    if (dev && ctx->carry.empty() && ((uintptr_t)text & 15) == 0) {
+        dtext = text; // zero copy
+    } else if (total) {
+        CK(ctx->b_text.ensure(total + 64));
+        uint8_t* d = ctx->b_text.as<uint8_t>();
+        if (!ctx->carry.empty()) CK(cudaMemcpyAsync(d, ctx->carry.data(), ctx->carry.size(), cudaMemcpyHostToDevice, ctx->st));
+        if (nbytes) CK(cudaMemcpyAsync(d + ctx->carry.size(), text, nbytes, cudaMemcpyDefault, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st)); // carry is reused below
+        dtext = d;
+    }
+    size_t proc = total;
+    if (!last_chunk && total) {
+        // keep the unterminated tail for the next chunk (chunks need not end on newlines)
+        size_t scan = std::min<size_t>(total, 1 << 20);
+        std::vector<uint8_t> tail;
+        long long nlpos = -1;
+        for (;;) {
+            tail.resize(scan);
+            CK(cudaMemcpy(tail.data(), dtext + (total - scan), scan, cudaMemcpyDeviceToHost));
+            for (long long k = (long long)scan - 1; k >= 0; k--) if (tail[k] == '\n') { nlpos = (long long)(total - scan) + k; break; }
+            if (nlpos >= 0 || scan == total) break;
+            scan = std::min<size_t>(total, scan * 8);
+        }
+        proc = (size_t)(nlpos + 1);
+        size_t off_in_tail = proc - (total - scan);
+        ctx->carry.assign(tail.begin() + off_in_tail, tail.end());
+    } else {
+        ctx->carry.clear();
+    }
+    int st = tokenize_device(ctx, dtext, (int64_t)proc);
+    if (st) return st;
+    if (last_chunk) ctx->paf_done = true;
+    cudaEventRecord(ctx->ev[1], ctx->st);
+    CK(cudaStreamSynchronize(ctx->st));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_tokenize += ms;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_peek_first_record(raftgpu_ctx* ctx, const uint8_t* text, size_t nbytes, int32_t rec[6], int32_t* found)
+{
+    if (!ctx || !rec || !found) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "set reads first");
+    CK(cudaSetDevice(ctx->device));
+    *found = 0;
+    if (!nbytes) return RAFTGPU_OK;
+    size_t head = std::min<size_t>(nbytes, 4u << 20); // the first record sits at the very start of any sane PAF
+    for (;;) {
+        CK(ctx->b_text.ensure(head + 64));
+        CK(cudaMemcpyAsync(ctx->b_text.p, text, head, cudaMemcpyDefault, ctx->st));
+        launch_paf_peek(ctx->b_text.as<uint8_t>(), (int64_t)head, ctx->nt, ctx->misc()->rec0, &ctx->misc()->err, ctx->st);
+        CKL();
+        int r[8];
+        CK(cudaMemcpyAsync(r, ctx->misc()->rec0, sizeof r, cudaMemcpyDeviceToHost, ctx->st));
+        int st = fetch_err(ctx);
+        if (st) return st;
+        if (r[6] || head == nbytes) { for (int k = 0; k < 6; k++) rec[k] = r[k]; *found = r[6]; break; }
+        head = std::min<size_t>(nbytes, head * 8);
+    }
+    // leave rec0 unset on the device: the caller decides through raftgpu_set_first_record
+    int zero = 0;
+    CK(cudaMemcpy(&ctx->misc()->rec0[6], &zero, sizeof zero, cudaMemcpyHostToDevice));
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_set_first_record(raftgpu_ctx* ctx, const int32_t rec[6], int32_t is_local)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int r[8] = {0};
+    if (rec) { for (int k = 0; k < 6; k++) r[k] = rec[k]; r[6] = 1; }
+    CK(cudaMemcpy(ctx->misc()->rec0, r, sizeof r, cudaMemcpyHostToDevice));
+    ctx->rec0_external = true; ctx->first_is_local = is_local != 0;
+    return RAFTGPU_OK;
+}
+extern "C" int raftgpu_get_symmetric(raftgpu_ctx* ctx, int32_t* flag)
+{
+    if (!ctx || !flag) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaMemcpy(flag, &ctx->misc()->sym_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    return RAFTGPU_OK;
+}
+extern "C" int raftgpu_set_symmetric(raftgpu_ctx* ctx, int32_t flag)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int f = flag != 0;
+    CK(cudaMemcpy(&ctx->misc()->sym_flag, &f, sizeof(int), cudaMemcpyHostToDevice));
+    ctx->sym_external = true;
+    return RAFTGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ coverage
+static ScatterArgs scatter_args(raftgpu_ctx* ctx)
+{
+    ScatterArgs a{};
+    a.qid = ctx->b_qid.as<int32_t>(); a.tid = ctx->b_tid.as<int32_t>(); a.qs = ctx->b_qs.as<int32_t>(); a.qe = ctx->b_qe.as<int32_t>();
+    a.ts = ctx->b_ts.as<int32_t>(); a.te = ctx->b_te.as<int32_t>(); a.n_rec = ctx->n_rec;
+    a.slot_off = ctx->b_slot_off.as<int64_t>(); a.diff = ctx->b_cov.as<int32_t>(); a.reso = ctx->prm.reso;
+    a.own_first = ctx->own_first; a.own_count = ctx->m; a.sym_flag = &ctx->misc()->sym_flag; a.err = &ctx->misc()->err;
+    return a;
+}
+
+static int zero_diff(raftgpu_ctx* ctx)
+{
+    if (ctx->diff_zeroed) return RAFTGPU_OK;
+    CK(ctx->b_cov.ensure(sizeof(int32_t) * (size_t)(ctx->n_slots + 8)));
+    CK(cudaMemsetAsync(ctx->b_cov.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st));
+    ctx->diff_zeroed = true;
+    return RAFTGPU_OK;
+}
+
+static int accumulate_local(raftgpu_ctx* ctx)
+{
+    int st = zero_diff(ctx);
+    if (st) return st;
+    launch_scatter_records(scatter_args(ctx), ctx->st);
+    CKL();
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_accumulate_endpoints(raftgpu_ctx* ctx, const void* ep, int64_t count)
+{
+    if (!ctx || count < 0 || (count && !ep)) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads || ctx->finalized) FAIL(RAFTGPU_E_STATE, "raftgpu_accumulate_endpoints: wrong state");
+    CK(cudaSetDevice(ctx->device));
+    int st = zero_diff(ctx);
+    if (st) return st;
+    launch_scatter_endpoints((const int32_t*)ep, count, ctx->b_slot_off.as<int64_t>(), ctx->b_cov.as<int32_t>(), ctx->prm.reso, ctx->own_first,
+                             ctx->m, &ctx->misc()->err, ctx->st);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_route_count(raftgpu_ctx* ctx, int nranks, const int64_t* bounds, int64_t* counts)
+{
+    if (!ctx || nranks < 1 || nranks > 64 || !bounds || !counts) return RAFTGPU_E_ARG;
+    if (!ctx->paf_done) FAIL(RAFTGPU_E_STATE, "raftgpu_route_count: finish PAF ingest first");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf db;
+    CK(db.ensure(sizeof(int64_t) * (nranks + 1)));
+    CK(cudaMemcpyAsync(db.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->misc()->route_counts, 0, sizeof(unsigned long long) * 64, ctx->st));
+    launch_route_count(scatter_args(ctx), nranks, db.as<int64_t>(), ctx->misc()->route_counts, ctx->st);
+    CKL();
+    CK(cudaMemcpyAsync(counts, ctx->misc()->route_counts, sizeof(int64_t) * nranks, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_route_pack(raftgpu_ctx* ctx, int nranks, const int64_t* bounds, const int64_t* counts, void* sendbuf)
+{
+    if (!ctx || nranks < 1 || nranks > 64 || !bounds || !counts) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf db;
+    CK(db.ensure(sizeof(int64_t) * (nranks + 1)));
+    CK(cudaMemcpyAsync(db.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
+    unsigned long long cur[64] = {0};
+    for (int r = 1; r < nranks; r++) cur[r] = cur[r - 1] + (unsigned long long)counts[r - 1];
+    CK(cudaMemcpyAsync(ctx->misc()->route_counts, cur, sizeof cur, cudaMemcpyHostToDevice, ctx->st));
+    launch_route_pack(scatter_args(ctx), nranks, db.as<int64_t>(), ctx->misc()->route_counts, (int32_t*)sendbuf, ctx->st);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));
+    return RAFTGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+static int layout_outputs(raftgpu_ctx* ctx);
+
+extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "raftgpu_finalize: no reads");
+    if (ctx->finalized) FAIL(RAFTGPU_E_STATE, "raftgpu_finalize: already finalized");
+    CK(cudaSetDevice(ctx->device));
+    const raftgpu_params& P = ctx->prm;
+    Misc* M = ctx->misc();
+    int st = zero_diff(ctx);
+    if (st) return st;
+    const int64_t m = ctx->m;
+    // K2b: coverage = inclusive scan of the difference array
+    cudaEventRecord(ctx->ev[3], ctx->st);
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_cov(ctx->n_slots) + scan_tiles_small(std::max<int64_t>(m, ctx->cut_cap_total + m)) + 16)));
+    launch_scan_cov_inplace(ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    cudaEventRecord(ctx->ev[4], ctx->st);
+    // K3: repeats + cut points
+    const int H = (int)(P.est_cov * P.cov_mul); // repeat.hpp:89-90: int * double, truncated
+    CK(ctx->b_rep.ensure(sizeof(int2) * (size_t)(ctx->rep_cap_total + 1))); CK(ctx->b_rep_cnt.ensure(sizeof(int32_t) * (size_t)(m + 1)));
+    CK(ctx->b_cuts.ensure(sizeof(int32_t) * (size_t)(ctx->cut_cap_total + 1))); CK(ctx->b_frag_cnt.ensure(sizeof(int32_t) * (size_t)(m + 1)));
+    CK(cudaMemsetAsync(&M->work_counter, 0, sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(M->stats, 0, sizeof M->stats, ctx->st));
+    RepeatCutArgs ra{};
+    ra.cov = ctx->b_cov.as<int32_t>(); ra.slot_off = ctx->b_slot_off.as<int64_t>(); ra.seq_off = ctx->d_seq_off; ra.m = m;
+    ra.reso = P.reso; ra.H = H; ra.p = P.repeat_length; ra.P = P.interval_length; ra.f = P.flanking_length; ra.l = P.read_length;
+    ra.rep_cap_off = ctx->b_rep_cap_off.as<int64_t>(); ra.cut_cap_off = ctx->b_cut_cap_off.as<int64_t>();
+    ra.rep = ctx->b_rep.as<int2>(); ra.rep_cnt = ctx->b_rep_cnt.as<int32_t>(); ra.cuts = ctx->b_cuts.as<int32_t>();
+    ra.frag_cnt = ctx->b_frag_cnt.as<int32_t>(); ra.stats = M->stats; ra.work_counter = &M->work_counter;
+    launch_repeat_cut(ra, ctx->st);
+    CKL();
+    cudaEventRecord(ctx->ev[5], ctx->st);
+    // fragment numbering inside this context
+    CK(ctx->b_frag_base.ensure(sizeof(int64_t) * (size_t)(m + 1)));
+    launch_scan_i32_to_i64(ctx->b_frag_cnt.as<int32_t>(), ctx->b_frag_base.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    CK(ctx->b_rep_off.ensure(sizeof(int64_t) * (size_t)(m + 1)));
+    launch_scan_i32_to_i64(ctx->b_rep_cnt.as<int32_t>(), ctx->b_rep_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    long long G = 0, R = 0, nrec = ctx->n_rec;
+    int       S = 0;
+    unsigned long long stats2[2];
+    CK(cudaMemcpyAsync(&G, ctx->b_frag_base.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&R, ctx->b_rep_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&S, &M->sym_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(stats2, M->stats, sizeof stats2, cudaMemcpyDeviceToHost, ctx->st));
+    if ((st = fetch_err(ctx))) return st;
+    ctx->G = G; ctx->n_repeats = R; ctx->finalized = true;
+    raftgpu_stats& s = ctx->stats;
+    s.n_reads = ctx->n; s.n_records = nrec; s.symmetric = S; s.high_cov = H; s.real_reads = ctx->real_reads;
+    s.n_bins = ctx->n_slots - m;
+    s.total_windows = (int32_t)(uint32_t)(uint64_t)s.n_bins; // int counter in the reference (repeat.hpp:95,117)
+    s.total_cov = (int64_t)stats2[0]; s.total_repeat_len = (int64_t)stats2[1]; s.total_read_len = ctx->total_read_len;
+    s.n_repeats = R; s.n_fragments = G;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); s.ms_scan = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); s.ms_repeat_cut = ms;
+    s.kernel_launches = ctx->launches;
+    if (out) *out = s;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_set_output_base(raftgpu_ctx* ctx, int64_t first_read_num)
+{
+    if (!ctx || first_read_num < 1) return RAFTGPU_E_ARG;
+    if (!ctx->finalized) FAIL(RAFTGPU_E_STATE, "raftgpu_set_output_base: finalize first");
+    ctx->read_num_base = first_read_num - 1;
+    ctx->sized = false;
+    return RAFTGPU_OK;
+}
+
+// sizes and offsets of the three output streams
+static int layout_outputs(raftgpu_ctx* ctx)
+{
+    if (ctx->sized) return RAFTGPU_OK;
+    if (!ctx->finalized) FAIL(RAFTGPU_E_STATE, "outputs requested before raftgpu_run / raftgpu_finalize");
+    CK(cudaSetDevice(ctx->device));
+    Misc* M = ctx->misc();
+    const int64_t m = ctx->m, G = ctx->G;
+    cudaEventRecord(ctx->ev[6], ctx->st);
+    // fragments
+    CK(ctx->b_frag_read.ensure(sizeof(int32_t) * (size_t)(G + 1))); CK(ctx->b_frag_a.ensure(sizeof(int32_t) * (size_t)(G + 1)));
+    CK(ctx->b_frag_b.ensure(sizeof(int32_t) * (size_t)(G + 1)));    CK(ctx->b_frag_size.ensure(sizeof(int32_t) * (size_t)(G + 1)));
+    CK(ctx->b_frag_off.ensure(sizeof(int64_t) * (size_t)(G + 1)));
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_small(std::max<int64_t>(G, m)) + cov_tiles(ctx->n_slots) / 256 + 64)));
+    FragExpandArgs fa{};
+    fa.m = m; fa.seq_off = ctx->d_seq_off; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first;
+    fa.cut_cap_off = ctx->b_cut_cap_off.as<int64_t>(); fa.cuts = ctx->b_cuts.as<int32_t>(); fa.frag_cnt = ctx->b_frag_cnt.as<int32_t>();
+    fa.frag_base = ctx->b_frag_base.as<int64_t>(); fa.v = ctx->prm.overlap_length; fa.read_num_base = ctx->read_num_base;
+    fa.frag_read = ctx->b_frag_read.as<int32_t>(); fa.frag_a = ctx->b_frag_a.as<int32_t>(); fa.frag_b = ctx->b_frag_b.as<int32_t>();
+    fa.frag_size = ctx->b_frag_size.as<int32_t>(); fa.err = &M->err;
+    launch_frag_expand(fa, ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_frag_size.as<int32_t>(), ctx->b_frag_off.as<int64_t>(), G, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    // long_repeats.txt lines
+    CK(ctx->b_rep_line_size.ensure(sizeof(int32_t) * (size_t)(m + 1))); CK(ctx->b_rep_line_off.ensure(sizeof(int64_t) * (size_t)(m + 1)));
+    launch_rep_sizes(ctx->b_rep_cnt.as<int32_t>(), ctx->b_rep_cap_off.as<int64_t>(), ctx->b_rep.as<int2>(), m, ctx->own_first,
+                     ctx->b_rep_line_size.as<int32_t>(), ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_rep_line_size.as<int32_t>(), ctx->b_rep_line_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    // coverage.txt tiles
+    const int T = cov_tiles(ctx->n_slots);
+    CK(ctx->b_cov_tile_bytes.ensure(sizeof(int32_t) * (size_t)(T + 1))); CK(ctx->b_cov_tile_off.ensure(sizeof(int64_t) * (size_t)(T + 1)));
+    CovEmitArgs ca{};
+    ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
+    ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_bytes = ctx->b_cov_tile_bytes.as<int32_t>(); ca.tile_first = 0;
+    launch_cov_sizes(ca, ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_off.as<int64_t>(), T, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    ctx->h_cov_tile_off.resize(T + 1); ctx->h_rep_line_off.resize(m + 1);
+    long long fasta_bytes = 0;
+    CK(cudaMemcpyAsync(ctx->h_cov_tile_off.data(), ctx->b_cov_tile_off.p, sizeof(int64_t) * (T + 1), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_rep_line_off.data(), ctx->b_rep_line_off.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&fasta_bytes, ctx->b_frag_off.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, ctx->st));
+    cudaEventRecord(ctx->ev[7], ctx->st);
+    int st = fetch_err(ctx);
+    if (st) return st;
+    raftgpu_stats& s = ctx->stats;
+    s.out_bytes[RAFTGPU_OUT_COVERAGE] = (uint64_t)ctx->h_cov_tile_off[T];
+    s.out_bytes[RAFTGPU_OUT_LONG_REPEATS] = (uint64_t)ctx->h_rep_line_off[m];
+    s.out_bytes[RAFTGPU_OUT_BED] = 0; // real reads: the file is created empty (repeat.hpp:87,187)
+    s.out_bytes[RAFTGPU_OUT_READS_FASTA] = (uint64_t)fasta_bytes;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); s.ms_layout = ms;
+    s.kernel_launches = ctx->launches;
+    ctx->sized = true;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_run(raftgpu_ctx* ctx, raftgpu_stats* out)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "raftgpu_run: no reads");
+    if (!ctx->paf_done) { // allow a PAF whose last chunk was not flagged: flush the carry
+        int st = raftgpu_ingest_paf(ctx, nullptr, 0, 1);
+        if (st) return st;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev[2], ctx->st);
+    int st = accumulate_local(ctx);
+    if (st) return st;
+    cudaEventRecord(ctx->ev[3], ctx->st);
+    if ((st = raftgpu_finalize(ctx, nullptr))) return st;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_scatter = ms;
+    if ((st = layout_outputs(ctx))) return st;
+    raftgpu_stats& s = ctx->stats;
+    s.ms_total = s.ms_tokenize + s.ms_scatter + s.ms_scan + s.ms_repeat_cut + s.ms_layout;
+    if (out) *out = s;
+    return RAFTGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ outputs
+// materialise stream bytes [w0, w1) of `which` at device address d (d[k] = stream byte w0+k)
+static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st)
+{
+    if (w1 <= w0) return RAFTGPU_OK;
+    const int64_t m = ctx->m;
+    if (which == RAFTGPU_OUT_COVERAGE) {
+        const auto& off = ctx->h_cov_tile_off;
+        int64_t t0 = std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1;
+        int64_t t1 = std::lower_bound(off.begin(), off.end(), w1) - off.begin();
+        CovEmitArgs ca{};
+        ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
+        ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
+        ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0;
+        launch_cov_emit(ca, t1 - t0, st);
+        CKL();
+    } else if (which == RAFTGPU_OUT_LONG_REPEATS) {
+        const auto& off = ctx->h_rep_line_off;
+        int64_t r0 = std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1;
+        int64_t r1 = std::lower_bound(off.begin(), off.end(), w1) - off.begin();
+        RepEmitArgs ra{};
+        ra.rep_cnt = ctx->b_rep_cnt.as<int32_t>(); ra.rep_cap_off = ctx->b_rep_cap_off.as<int64_t>(); ra.rep = ctx->b_rep.as<int2>();
+        ra.line_off = ctx->b_rep_line_off.as<int64_t>(); ra.m = m; ra.own_first = ctx->own_first; ra.dst = d; ra.w0 = w0; ra.w1 = w1;
+        ra.read_first = r0; ra.read_last = std::min<int64_t>(r1, m);
+        launch_rep_emit(ra, st);
+        CKL();
+    } else if (which == RAFTGPU_OUT_READS_FASTA) {
+        if (!ctx->have_seq) FAIL(RAFTGPU_E_STATE, "reads.fasta requested but no sequence bytes were given");
+        if (!ctx->real_reads) FAIL(RAFTGPU_E_UNSUPPORTED, "simulated-read headers (chop.hpp:252-258,293-310) are not emitted by the device path");
+        FastaEmitArgs fa{};
+        fa.frag_read = ctx->b_frag_read.as<int32_t>(); fa.frag_a = ctx->b_frag_a.as<int32_t>(); fa.frag_b = ctx->b_frag_b.as<int32_t>();
+        fa.frag_off = ctx->b_frag_off.as<int64_t>(); fa.G = ctx->G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
+        fa.names = ctx->d_names; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first; fa.read_num_base = ctx->read_num_base;
+        fa.dst = d; fa.w0 = w0; fa.w1 = w1;
+        launch_fasta_emit(fa, st);
+        CKL();
+    }
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_output_size(raftgpu_ctx* ctx, int which, uint64_t* nbytes)
+{
+    if (!ctx || !nbytes || which < 0 || which > 3) return RAFTGPU_E_ARG;
+    int st = layout_outputs(ctx);
+    if (st) return st;
+    *nbytes = ctx->stats.out_bytes[which];
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t* dst, size_t n)
+{
+    if (!ctx || which < 0 || which > 3 || (!dst && n)) return RAFTGPU_E_ARG;
+    int st = layout_outputs(ctx);
+    if (st) return st;
+    if (off + n > ctx->stats.out_bytes[which]) return RAFTGPU_E_ARG;
+    if (!n) return RAFTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (is_device_ptr(dst)) {
+        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst, ctx->st))) return st;
+        CK(cudaStreamSynchronize(ctx->st));
+        return fetch_err(ctx);
+    }
+    // host destination: double-buffered windows, emit on st, copy out on st2
+    const size_t W = std::min<size_t>(WINDOW_BYTES, n);
+    for (int k = 0; k < 2; k++) CK(ctx->b_stage[k].ensure(W + 64));
+    size_t done = 0;
+    int    k = 0;
+    bool   used[2] = {false, false};
+    while (done < n) {
+        size_t len = std::min(W, n - done);
+        if (used[k]) CK(cudaEventSynchronize(ctx->ev_stage[k])); // the copy out of this buffer has finished
+        if ((st = emit_window(ctx, which, (int64_t)(off + done), (int64_t)(off + done + len), ctx->b_stage[k].as<uint8_t>(), ctx->st))) return st;
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaMemcpyAsync(dst + done, ctx->b_stage[k].p, len, cudaMemcpyDeviceToHost, ctx->st2));
+        CK(cudaEventRecord(ctx->ev_stage[k], ctx->st2));
+        used[k] = true;
+        done += len; k ^= 1;
+    }
+    CK(cudaStreamSynchronize(ctx->st2));
+    return fetch_err(ctx);
+}
+
+extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest)
+{
+    if (!ctx || !digest || which < 0 || which > 3) return RAFTGPU_E_ARG;
+    int st = layout_outputs(ctx);
+    if (st) return st;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t total = ctx->stats.out_bytes[which];
+    const size_t   W = (size_t)std::min<uint64_t>(WINDOW_BYTES, std::max<uint64_t>(total, 1));
+    CK(ctx->b_stage[0].ensure(W + 64));
+    CK(cudaMemsetAsync(&ctx->misc()->digest, 0, sizeof(unsigned long long), ctx->st));
+    for (uint64_t off = 0; off < total; off += W) {
+        size_t len = (size_t)std::min<uint64_t>(W, total - off);
+        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + len), ctx->b_stage[0].as<uint8_t>(), ctx->st))) return st;
+        launch_digest(ctx->b_stage[0].as<uint8_t>(), (int64_t)len, (int64_t)off, &ctx->misc()->digest, ctx->st);
+        CKL();
+    }
+    unsigned long long d = 0;
+    CK(cudaMemcpyAsync(&d, &ctx->misc()->digest, sizeof d, cudaMemcpyDeviceToHost, ctx->st));
+    if ((st = fetch_err(ctx))) return st;
+    *digest = d;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_fetch_table(raftgpu_ctx* ctx, int table, void* dst, size_t cap_bytes, size_t* n_elems)
+{
+    if (!ctx || table < 0 || table >= RAFTGPU_TAB_COUNT || !n_elems) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    const int64_t m = ctx->m;
+    size_t elem = 4, count = 0;
+    std::vector<uint8_t> host; // tables assembled on the host
+    const void* dsrc = nullptr;
+    if (table <= RAFTGPU_TAB_STRAND) {
+        const DevBuf* cols[] = {&ctx->b_qid, &ctx->b_tid, &ctx->b_qs, &ctx->b_qe, &ctx->b_ts, &ctx->b_te, &ctx->b_strand};
+        elem = table == RAFTGPU_TAB_STRAND ? 1 : 4; count = (size_t)ctx->n_rec; dsrc = cols[table]->p;
+    } else if (table == RAFTGPU_TAB_BIN_OFF || table == RAFTGPU_TAB_COV) {
+        if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "no reads");
+        std::vector<int64_t> so(m + 1);
+        CK(cudaMemcpy(so.data(), ctx->b_slot_off.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost));
+        if (table == RAFTGPU_TAB_BIN_OFF) {
+            elem = 8; count = (size_t)m + 1; host.resize(count * 8);
+            int64_t* o = (int64_t*)host.data();
+            for (int64_t i = 0; i <= m; i++) o[i] = so[i] - i;
+        } else {
+            if (!ctx->finalized) FAIL(RAFTGPU_E_STATE, "coverage requested before raftgpu_run");
+            elem = 4; count = (size_t)(ctx->n_slots - m);
+            if (dst) {
+                std::vector<int32_t> slots((size_t)ctx->n_slots);
+                if (ctx->n_slots) CK(cudaMemcpy(slots.data(), ctx->b_cov.p, sizeof(int32_t) * (size_t)ctx->n_slots, cudaMemcpyDeviceToHost));
+                host.resize(count * 4);
+                int32_t* o = (int32_t*)host.data();
+                for (int64_t i = 0; i < m; i++) { int64_t nb = so[i + 1] - so[i] - 1; if (nb) memcpy(o + (so[i] - i), slots.data() + so[i], sizeof(int32_t) * (size_t)nb); }
+            }
+        }
+    } else if (table == RAFTGPU_TAB_REP_OFF) {
+        if (!ctx->finalized) FAIL(RAFTGPU_E_STATE, "repeats requested before raftgpu_run");
+        elem = 8; count = (size_t)m + 1; dsrc = ctx->b_rep_off.p;
+    } else if (table == RAFTGPU_TAB_REP) {
+        if (!ctx->finalized) FAIL(RAFTGPU_E_STATE, "repeats requested before raftgpu_run");
+        elem = 4; count = (size_t)ctx->n_repeats * 2;
+        if (dst && count) {
+            DevBuf tmp;
+            CK(tmp.ensure(count * 4));
+            launch_rep_compact(ctx->b_rep_cnt.as<int32_t>(), ctx->b_rep_cap_off.as<int64_t>(), ctx->b_rep_off.as<int64_t>(), ctx->b_rep.as<int2>(), m,
+                               tmp.as<int32_t>(), ctx->st);
+            CKL();
+            host.resize(count * 4);
+            CK(cudaMemcpyAsync(host.data(), tmp.p, count * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+        }
+    } else if (table == RAFTGPU_TAB_FRAG) {
+        int st = layout_outputs(ctx);
+        if (st) return st;
+        elem = 4; count = (size_t)ctx->G * 3;
+        if (dst && count) {
+            std::vector<int32_t> r(ctx->G), a(ctx->G), b(ctx->G);
+            CK(cudaMemcpy(r.data(), ctx->b_frag_read.p, 4 * (size_t)ctx->G, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(a.data(), ctx->b_frag_a.p, 4 * (size_t)ctx->G, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(b.data(), ctx->b_frag_b.p, 4 * (size_t)ctx->G, cudaMemcpyDeviceToHost));
+            host.resize(count * 4);
+            int32_t* o = (int32_t*)host.data();
+            for (int64_t g = 0; g < ctx->G; g++) { o[3 * g] = (int32_t)(r[g] + ctx->own_first); o[3 * g + 1] = a[g]; o[3 * g + 2] = b[g]; }
+        }
+    }
+    *n_elems = count;
+    if (!dst) return RAFTGPU_OK;
+    if (cap_bytes < count * elem) return RAFTGPU_E_ARG;
+    if (count) {
+        if (!host.empty()) CK(cudaMemcpy(dst, host.data(), count * elem, cudaMemcpyDefault));
+        else CK(cudaMemcpy(dst, dsrc, count * elem, cudaMemcpyDefault));
+    }
+    return RAFTGPU_OK;
+}

@@ -1,0 +1,261 @@
+// host_io.cpp — host side of the boundary: FASTA/FASTQ(+gz) reader and the file-level drop-in for
+// break_long_reads (chop.hpp:331-373).  No compute here: everything numeric happens on the device
+// through the C ABI in include/raft_b200.h.
+#include <zlib.h>
+
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../include/raft_b200.h"
+
+namespace {
+
+// Streaming FASTA/FASTQ record reader with the record grammar of kseq_read (kseq.h:240-298) as used
+// by loadFASTA (chop.hpp:88-131): name = header up to the first isspace byte, the rest of the header
+// line is a comment, sequence = following lines joined (blank lines skipped, a trailing '\r' of a line
+// dropped once more than one byte has been collected), a '+' line switches to FASTQ quality which
+// must reach the sequence length.  Lengths and names stop at an embedded NUL (strlen / std::string).
+class SeqReader {
+public:
+    std::vector<uint8_t> seq, names;
+    std::vector<int64_t> seq_off{0}, name_off{0};
+    bool                 fastq_truncated = false;
+
+    void feed(const uint8_t* p, size_t n)
+    {
+        size_t i = 0;
+        while (i < n && !stopped_) {
+            switch (st_) {
+            case SEEK:
+                while (i < n && p[i] != '>' && p[i] != '@') i++;
+                if (i < n) { i++; begin_record(); }
+                break;
+            case NAME:
+                any_after_marker_ = true;
+                while (i < n && !is_space(p[i])) name_.push_back((char)p[i++]);
+                if (i < n) { st_ = (p[i] == '\n') ? SEQ_BOL : COMMENT; i++; }
+                break;
+            case COMMENT:
+                while (i < n && p[i] != '\n') i++;
+                if (i < n) { i++; st_ = SEQ_BOL; }
+                break;
+            case SEQ_BOL: {
+                uint8_t c = p[i++];
+                if (c == '>' || c == '@') { end_record(); begin_record(); }
+                else if (c == '+') st_ = PLUS;
+                else if (c == '\n') {}
+                else { cur_.push_back(c); st_ = SEQ_LINE; }
+                break;
+            }
+            case SEQ_LINE: {
+                const uint8_t* e = (const uint8_t*)memchr(p + i, '\n', n - i);
+                size_t         k = e ? (size_t)(e - p) : n;
+                cur_.insert(cur_.end(), p + i, p + k);
+                i = k;
+                if (e) { i++; strip_cr(cur_); st_ = SEQ_BOL; }
+                break;
+            }
+            case PLUS:
+                while (i < n && p[i] != '\n') i++;
+                if (i < n) { i++; st_ = QUAL; qual_len_ = 0; qual_last_ = 0; qual_lines_ = 0; }
+                break;
+            case QUAL: {
+                // kseq.h:292: read lines while the quality is shorter than the sequence
+                if (qual_lines_ > 0 && qual_len_ >= cur_.size()) { end_fastq(); break; }
+                const uint8_t* e = (const uint8_t*)memchr(p + i, '\n', n - i);
+                size_t         k = e ? (size_t)(e - p) : n;
+                if (k > i) { qual_len_ += k - i; qual_last_ = p[k - 1]; }
+                i = k;
+                if (e) {
+                    i++;
+                    if (qual_len_ > 1 && qual_last_ == '\r') { qual_len_--; qual_last_ = 0; }
+                    qual_lines_++;
+                    if (qual_len_ >= cur_.size()) end_fastq();
+                }
+                break;
+            }
+            }
+        }
+    }
+
+    void finish()
+    {
+        if (stopped_) return;
+        switch (st_) {
+        case SEEK: break;
+        case NAME: if (any_after_marker_) end_record(); break; // EOF right after the marker: no record (kseq.h:254-255)
+        case COMMENT: case SEQ_BOL: end_record(); break;
+        case SEQ_LINE: strip_cr(cur_); end_record(); break;
+        case PLUS: fastq_truncated = true; break;               // kseq.h:288-289
+        case QUAL:
+            if (qual_len_ > 1 && qual_last_ == '\r') qual_len_--;
+            end_fastq();
+            break;
+        }
+        st_ = SEEK;
+    }
+
+private:
+    enum St { SEEK, NAME, COMMENT, SEQ_BOL, SEQ_LINE, PLUS, QUAL } st_ = SEEK;
+    std::string          name_;
+    std::vector<uint8_t> cur_;
+    size_t               qual_len_ = 0, qual_lines_ = 0;
+    uint8_t              qual_last_ = 0;
+    bool                 any_after_marker_ = false, stopped_ = false;
+
+    static bool is_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+    static void strip_cr(std::vector<uint8_t>& s) { if (s.size() > 1 && s.back() == '\r') s.pop_back(); }
+    void begin_record() { name_.clear(); cur_.clear(); any_after_marker_ = false; st_ = NAME; }
+    void end_record()
+    {
+        size_t sl = strnlen((const char*)cur_.data(), cur_.size());
+        size_t nl = strnlen(name_.data(), name_.size());
+        seq.insert(seq.end(), cur_.begin(), cur_.begin() + sl);
+        names.insert(names.end(), name_.begin(), name_.begin() + nl);
+        seq_off.push_back((int64_t)seq.size());
+        name_off.push_back((int64_t)names.size());
+        st_ = SEEK;
+    }
+    void end_fastq()
+    {
+        if (qual_len_ != cur_.size()) { fastq_truncated = true; stopped_ = true; return; } // kseq.h:297-298: -2 ends loadFASTA's loop
+        end_record(); // last_char = 0: the next record is searched from the following byte (kseq.h:296)
+    }
+};
+
+template <typename T>
+T* steal(const std::vector<T>& v)
+{
+    T* p = (T*)malloc(sizeof(T) * (v.size() ? v.size() : 1));
+    if (p && !v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+bool file_missing_or_empty(const char* fn)
+{ // chop.hpp:326-349
+    std::ifstream f(fn);
+    return !f || f.peek() == std::ifstream::traits_type::eof();
+}
+
+} // namespace
+
+extern "C" void raftgpu_free_host(void* p) { free(p); }
+
+extern "C" int raftgpu_load_fasta(const char* path, int64_t* n, int64_t** seq_off, uint8_t** seq, int64_t** name_off, uint8_t** names)
+{
+    if (!path || !n || !seq_off || !seq || !name_off || !names) return RAFTGPU_E_ARG;
+    gzFile fp = gzopen(path, "r"); // transparent for plain files, like the reference (chop.hpp:93)
+    if (!fp) return RAFTGPU_E_IO;
+    gzbuffer(fp, 1 << 20);
+    SeqReader            rd;
+    std::vector<uint8_t> buf(8 << 20);
+    for (;;) {
+        int got = gzread(fp, buf.data(), (unsigned)buf.size());
+        if (got <= 0) break;
+        rd.feed(buf.data(), (size_t)got);
+    }
+    gzclose(fp);
+    rd.finish();
+    *n = (int64_t)rd.seq_off.size() - 1;
+    *seq_off = steal(rd.seq_off); *name_off = steal(rd.name_off);
+    *seq = steal(rd.seq); *names = steal(rd.names);
+    if (!*seq_off || !*name_off || !*seq || !*names) return RAFTGPU_E_NOMEM;
+    return RAFTGPU_OK;
+}
+
+static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, std::string& err)
+{
+    uint64_t total = 0;
+    if (raftgpu_output_size(ctx, which, &total)) { err = raftgpu_last_error(ctx); return false; }
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot open " + path; return false; }
+    const size_t         W = 512u << 20;
+    std::vector<uint8_t> buf((size_t)std::min<uint64_t>(W, total ? total : 1));
+    for (uint64_t off = 0; off < total; off += W) {
+        size_t len = (size_t)std::min<uint64_t>(W, total - off);
+        int    st = raftgpu_fetch(ctx, which, off, buf.data(), len);
+        if (st) { err = std::string(raftgpu_strerror(st)) + ": " + raftgpu_last_error(ctx); fclose(f); return false; }
+        if (fwrite(buf.data(), 1, len, f) != len) { err = "short write to " + path; fclose(f); return false; }
+    }
+    fclose(f);
+    return true;
+}
+
+extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* paffilename, const raftgpu_params* p, const char* prefix,
+                                        int device, raftgpu_stats* stats_out)
+{
+    if (!readfilename || !paffilename || !p || !prefix) return RAFTGPU_E_ARG;
+    const std::string pre(prefix);
+    { std::ofstream touch(pre + ".reads.fasta"); } // chop.hpp:333: created before the inputs are validated
+    if (file_missing_or_empty(readfilename)) {
+        printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", readfilename);
+        return RAFTGPU_E_IO;
+    }
+    if (file_missing_or_empty(paffilename)) {
+        printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", paffilename);
+        return RAFTGPU_E_IO;
+    }
+    raftgpu_ctx* ctx = nullptr;
+    int          st = raftgpu_create(p, device, &ctx);
+    if (st) { fprintf(stderr, "raft_b200: %s\n", raftgpu_strerror(st)); return st; }
+    auto fail = [&](int code) {
+        fprintf(stderr, "raft_b200: %s: %s\n", raftgpu_strerror(code), raftgpu_last_error(ctx));
+        raftgpu_destroy(ctx);
+        return code;
+    };
+
+    int64_t  n = 0;
+    int64_t *seq_off = nullptr, *name_off = nullptr;
+    uint8_t *seq = nullptr, *names = nullptr;
+    if ((st = raftgpu_load_fasta(readfilename, &n, &seq_off, &seq, &name_off, &names))) return fail(st);
+    st = raftgpu_set_reads(ctx, n, seq_off, seq, name_off, names);
+    free(seq_off); free(seq); free(name_off); free(names);
+    raftgpu_stats s{};
+    if (st) return fail(st);
+
+    // PAF: inflate (or read) in chunks and hand them to the tokenizer (paf.hpp:24-38 uses gzopen/gzread too)
+    {
+        gzFile fp = gzopen(paffilename, "r");
+        if (!fp) return fail(RAFTGPU_E_IO);
+        gzbuffer(fp, 1 << 20);
+        std::vector<uint8_t> buf(256u << 20);
+        for (;;) {
+            size_t fill = 0;
+            while (fill < buf.size()) {
+                int got = gzread(fp, buf.data() + fill, (unsigned)std::min<size_t>(buf.size() - fill, 1u << 30));
+                if (got <= 0) break;
+                fill += (size_t)got;
+            }
+            bool last = fill < buf.size();
+            if ((st = raftgpu_ingest_paf(ctx, buf.data(), fill, last ? 1 : 0))) { gzclose(fp); return fail(st); }
+            if (last) break;
+        }
+        gzclose(fp);
+    }
+    if ((st = raftgpu_run(ctx, &s))) {
+        // the reference prints these before it would have crashed; keep stdout comparable up to the failure
+        return fail(st);
+    }
+    printf("Real Reads %d \n", s.real_reads);                              // chop.hpp:105
+    printf("INFO, Symmetric overlaps %d \n", s.symmetric);                 // chop.hpp:189
+    printf("INFO, length of alignments  %d()\n", (int)s.n_records);        // chop.hpp:190
+    printf("high_cov %d\n", s.high_cov);                                   // repeat.hpp:91
+    double coverage_per_window = (double)s.total_cov / s.total_windows;    // repeat.hpp:173-178
+    double fraction_of_repeat_length = (double)s.total_repeat_len / s.total_read_len;
+    printf("coverage per window is %f \n", coverage_per_window);
+    printf("coverage per window/average coverage is %f \n", coverage_per_window / p->est_cov);
+    printf("fraction_of_repeat_length %f \n", fraction_of_repeat_length);
+
+    std::string err;
+    const char* suf[4] = {".coverage.txt", ".long_repeats.txt", ".long_repeats.bed", ".reads.fasta"};
+    for (int w = 0; w < 4; w++)
+        if (!write_stream(ctx, w, pre + suf[w], err)) { fprintf(stderr, "raft_b200: %s\n", err.c_str()); raftgpu_destroy(ctx); return RAFTGPU_E_IO; }
+    if (stats_out) *stats_out = s;
+    raftgpu_destroy(ctx);
+    return RAFTGPU_OK;
+}

@@ -1,0 +1,279 @@
+// k2_coverage.cu — K2: per-read bin coverage.
+//
+// Replaces profileCoverage (repeat.hpp:28-79).  The reference sorts a read's intervals and
+// increments every covered bin; here each contributing interval adds +1 at its first bin and -1
+// one past its last bin in a per-read difference array, and one device-wide inclusive scan turns
+// the array into coverage.  Every read owns nb+1 slots (nb = ceil(L/reso), repeat.hpp:32-37) so
+// each read's slots sum to zero and a plain (unsegmented) scan restarts at 0 on every read
+// boundary: no head flags, no segmented operator.
+//
+// Which intervals contribute (repeat.hpp:48-58, chop.hpp:165-169): the query side of every record;
+// the target side too when overlaps are not symmetric and target != query.
+// Bin range of [s, e) (repeat.hpp:62-77): lo = max(s,0)/reso, bins lo..(e-1)/reso when e-1 >= lo*reso.
+#include "kernels.h"
+
+namespace raftk {
+
+// ---------------------------------------------------------------- per-read layout
+__global__ void k_read_layout(const int64_t* seq_off, int64_t m, int reso, int p, int P, int l, int32_t* slots, int32_t* rep_cap,
+                              int32_t* cut_cap)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int64_t L = seq_off[i + 1] - seq_off[i];
+    int64_t nb = (L + reso - 1) / reso;
+    slots[i] = (int32_t)(nb + 1);
+    // a repeat needs a run of >= ceil(p/reso) bins (repeat.hpp:125) and runs are separated by >= 1 bin
+    int64_t minbins = ((int64_t)p + reso - 1) / reso;
+    if (minbins < 1) minbins = 1;
+    rep_cap[i] = (int32_t)((nb + 1) / (minbins + 1));
+    // stars: 0, P, ..., floor(L/P)*P (+ L) (chop.hpp:209-223); fragments <= ceil((stars-1)/div) (chop.hpp:270-276)
+    int64_t nstars = L / P + 1 + (L % P != 0);
+    int64_t div = l / P;
+    int64_t fmax = (nstars - 1 + div - 1) / div;
+    if (fmax < 1) fmax = 1;
+    cut_cap[i] = (int32_t)(fmax - 1);
+}
+void launch_read_layout(const int64_t* seq_off, int64_t m, int reso, int p, int P, int l, int32_t* slots, int32_t* rep_cap, int32_t* cut_cap,
+                        cudaStream_t st)
+{
+    if (m > 0) k_read_layout<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(seq_off, m, reso, p, P, l, slots, rep_cap, cut_cap);
+}
+
+// ---------------------------------------------------------------- small scan: int32[n] -> exclusive int64[n+1]
+constexpr int SS_THREADS = 256;
+constexpr int SS_ITEMS = 8;
+constexpr int SS_TILE = SS_THREADS * SS_ITEMS;
+
+__global__ void __launch_bounds__(SS_THREADS) k_scan_i32_to_i64(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n,
+                                                                uint64_t* status, int* ticket)
+{
+    __shared__ long long ws[34];
+    __shared__ uint64_t  bcast;
+    __shared__ int       s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int     tile = s_tile;
+    const int64_t base = (int64_t)tile * SS_TILE + (int64_t)threadIdx.x * SS_ITEMS;
+    long long     v[SS_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SS_ITEMS; k++) { v[k] = (base + k < n) ? (long long)in[base + k] : 0ll; sum += v[k]; }
+    long long tot;
+    long long ex = block_exclusive_sum<long long, SS_THREADS>(sum, ws, &tot);
+    uint64_t  pre = lookback_block(status, tile, (uint64_t)tot, &bcast);
+    long long run = lb_signed(pre) + ex;
+#pragma unroll
+    for (int k = 0; k < SS_ITEMS; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) out[n] = run;
+    }
+    if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
+}
+int  scan_tiles_small(int64_t n) { return (int)((n + SS_TILE - 1) / SS_TILE) + (n == 0); }
+void launch_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, uint64_t* status, int* ticket, cudaStream_t st)
+{
+    int tiles = scan_tiles_small(n);
+    cudaMemsetAsync(status, 0, sizeof(uint64_t) * tiles, st);
+    cudaMemsetAsync(ticket, 0, sizeof(int), st);
+    k_scan_i32_to_i64<<<tiles, SS_THREADS, 0, st>>>(in, out, n, status, ticket);
+}
+
+// ---------------------------------------------------------------- coverage scan: in-place inclusive, int32
+// Tile = 256 threads x 16 ints; warp w owns 512 consecutive ints read as 4 rounds of fully
+// coalesced 128-bit loads (lane l of round r holds ints [w*512 + r*128 + 4l, +4)).
+constexpr int CS_THREADS = 256;
+constexpr int CS_ROUNDS = 4;
+constexpr int CS_TILE = CS_THREADS * 4 * CS_ROUNDS; // 4096 ints = 16 KiB
+
+__global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ data, int64_t n, uint64_t* status, int* ticket)
+{
+    __shared__ int      ws[34];
+    __shared__ uint64_t bcast;
+    __shared__ int      s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int     tile = s_tile, lane = lane_id(), warp = warp_id();
+    const int64_t tbase = (int64_t)tile * CS_TILE + (int64_t)warp * (128 * CS_ROUNDS);
+    int4          v[CS_ROUNDS];
+    int           rsum[CS_ROUNDS];
+    const bool    full = (int64_t)(tile + 1) * CS_TILE <= n;
+#pragma unroll
+    for (int r = 0; r < CS_ROUNDS; r++) {
+        int64_t i = tbase + r * 128 + lane * 4;
+        if (full) {
+            v[r] = *reinterpret_cast<const int4*>(data + i);
+        } else {
+            v[r].x = i + 0 < n ? data[i + 0] : 0; v[r].y = i + 1 < n ? data[i + 1] : 0;
+            v[r].z = i + 2 < n ? data[i + 2] : 0; v[r].w = i + 3 < n ? data[i + 3] : 0;
+        }
+        rsum[r] = v[r].x + v[r].y + v[r].z + v[r].w;
+    }
+    // lane-exclusive prefix inside each round, rounds chained
+    int lane_ex[CS_ROUNDS], wtot = 0;
+#pragma unroll
+    for (int r = 0; r < CS_ROUNDS; r++) {
+        int inc = warp_inclusive_sum(rsum[r]);
+        lane_ex[r] = wtot + inc - rsum[r];
+        wtot += __shfl_sync(FULL, inc, 31);
+    }
+    // block: exclusive prefix over warp totals (one value per warp, carried by lane 31's slot)
+    int btot;
+    int bex = block_exclusive_sum<int, CS_THREADS>(lane == 31 ? wtot : 0, ws, &btot);
+    int warp_ex = __shfl_sync(FULL, bex, 31) - 0; // lane 31's exclusive prefix == sum of earlier warps
+    uint64_t pre = lookback_block(status, tile, (uint64_t)(int64_t)btot, &bcast);
+    int      p0 = (int)lb_signed(pre) + warp_ex;
+#pragma unroll
+    for (int r = 0; r < CS_ROUNDS; r++) {
+        int64_t i = tbase + r * 128 + lane * 4;
+        int     a = p0 + lane_ex[r];
+        int4    o;
+        o.x = a + v[r].x; o.y = o.x + v[r].y; o.z = o.y + v[r].z; o.w = o.z + v[r].w;
+        if (full) {
+            *reinterpret_cast<int4*>(data + i) = o;
+        } else {
+            if (i + 0 < n) data[i + 0] = o.x; if (i + 1 < n) data[i + 1] = o.y;
+            if (i + 2 < n) data[i + 2] = o.z; if (i + 3 < n) data[i + 3] = o.w;
+        }
+    }
+}
+int  scan_tiles_cov(int64_t n) { return (int)((n + CS_TILE - 1) / CS_TILE); }
+void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, cudaStream_t st)
+{
+    int tiles = scan_tiles_cov(n);
+    if (tiles == 0) return;
+    cudaMemsetAsync(status, 0, sizeof(uint64_t) * tiles, st);
+    cudaMemsetAsync(ticket, 0, sizeof(int), st);
+    k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(data, n, status, ticket);
+}
+
+// ---------------------------------------------------------------- scatter
+__device__ __forceinline__ void err_min(ErrState* err, int code, long long index)
+{
+    long long old = atomicMin(&err->index, index);
+    if (index <= old) err->code = code;
+}
+
+// adds interval [s,e) of owned local read lr; returns false when it would leave the read's bins
+__device__ __forceinline__ bool add_interval(int32_t* diff, const int64_t* __restrict__ slot_off, int64_t lr, int s, int e, int reso)
+{
+    int64_t base = slot_off[lr];
+    int64_t nb = slot_off[lr + 1] - base - 1;
+    int64_t lo = (int64_t)(s < 0 ? 0 : s) / reso;
+    int64_t em = (int64_t)e - 1;
+    if (em < lo * reso) return true; // nothing covered (repeat.hpp:69 never true)
+    int64_t hi = em / reso;
+    if (hi >= nb) return false;
+    atomicAdd(diff + base + lo, 1);
+    atomicAdd(diff + base + hi + 1, -1);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_scatter_records(ScatterArgs a)
+{
+    const bool    sym = *a.sym_flag != 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.n_rec; k += stride) {
+        int     q = a.qid[k], t = a.tid[k];
+        int64_t lq = (int64_t)q - a.own_first;
+        if (lq >= 0 && lq < a.own_count)
+            if (!add_interval(a.diff, a.slot_off, lq, a.qs[k], a.qe[k], a.reso)) err_min(a.err, RAFTK_E_RANGE, k);
+        if (!sym && t != q) {
+            int64_t lt = (int64_t)t - a.own_first;
+            if (lt >= 0 && lt < a.own_count)
+                if (!add_interval(a.diff, a.slot_off, lt, a.ts[k], a.te[k], a.reso)) err_min(a.err, RAFTK_E_RANGE, k);
+        }
+    }
+}
+void launch_scatter_records(const ScatterArgs& a, cudaStream_t st)
+{
+    if (a.n_rec <= 0) return;
+    int64_t blocks = (a.n_rec + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_scatter_records<<<(unsigned)blocks, 256, 0, st>>>(a);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_endpoints(const int32_t* __restrict__ ep, int64_t n, const int64_t* slot_off, int32_t* diff,
+                                                            int reso, int64_t own_first, int64_t own_count, ErrState* err)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int64_t lr = (int64_t)ep[3 * k] - own_first;
+        if (lr < 0 || lr >= own_count) { err_min(err, RAFTK_E_RANGE, k); continue; }
+        if (!add_interval(diff, slot_off, lr, ep[3 * k + 1], ep[3 * k + 2], reso)) err_min(err, RAFTK_E_RANGE, k);
+    }
+}
+void launch_scatter_endpoints(const int32_t* ep, int64_t n, const int64_t* slot_off, int32_t* diff, int reso, int64_t own_first,
+                              int64_t own_count, ErrState* err, cudaStream_t st)
+{
+    if (n <= 0) return;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_scatter_endpoints<<<(unsigned)blocks, 256, 0, st>>>(ep, n, slot_off, diff, reso, own_first, own_count, err);
+}
+
+// ---------------------------------------------------------------- multi-GPU routing
+// Every contributing interval becomes one endpoint (global read id, s, e) for the rank owning the read.
+__device__ __forceinline__ int owner_of(const int64_t* __restrict__ bounds, int nranks, int64_t id)
+{
+    int lo = 0, hi = nranks; // bounds[lo] <= id < bounds[hi]
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (id >= bounds[mid]) lo = mid; else hi = mid; }
+    return lo;
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
+                                               int32_t* sendbuf)
+{
+    extern __shared__ unsigned long long s_cnt[]; // nranks block-local counts, then nranks block bases
+    const bool sym = *a.sym_flag != 0;
+    for (int r = threadIdx.x; r < nranks; r += blockDim.x) s_cnt[r] = 0;
+    __syncthreads();
+    // each block owns a contiguous chunk of records so that packing is deterministic per block
+    int64_t per = (a.n_rec + gridDim.x - 1) / gridDim.x;
+    int64_t k0 = (int64_t)blockIdx.x * per, k1 = k0 + per < a.n_rec ? k0 + per : a.n_rec;
+    // pass 1: count
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        int q = a.qid[k], t = a.tid[k];
+        atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull);
+        if (!sym && t != q) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
+    }
+    __syncthreads();
+    if (!PACK) {
+        for (int r = threadIdx.x; r < nranks; r += blockDim.x)
+            if (s_cnt[r]) atomicAdd(&counters[r], s_cnt[r]);
+        return;
+    }
+    // pass 2: reserve a range per destination, then write
+    for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
+        s_cnt[nranks + r] = s_cnt[r] ? atomicAdd(&counters[r], s_cnt[r]) : 0ull;
+        s_cnt[r] = 0;
+    }
+    __syncthreads();
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        int q = a.qid[k], t = a.tid[k];
+        {
+            int                d = owner_of(bounds, nranks, q);
+            unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
+            sendbuf[3 * slot] = q; sendbuf[3 * slot + 1] = a.qs[k]; sendbuf[3 * slot + 2] = a.qe[k];
+        }
+        if (!sym && t != q) {
+            int                d = owner_of(bounds, nranks, t);
+            unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
+            sendbuf[3 * slot] = t; sendbuf[3 * slot + 1] = a.ts[k]; sendbuf[3 * slot + 2] = a.te[k];
+        }
+    }
+}
+static unsigned route_blocks(int64_t n) { int64_t b = (n + 4095) / 4096; if (b < 1) b = 1; if (b > 148 * 8) b = 148 * 8; return (unsigned)b; }
+void launch_route_count(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* counts, cudaStream_t st)
+{
+    if (a.n_rec <= 0) return;
+    k_route<false><<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, counts, nullptr);
+}
+void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
+{
+    if (a.n_rec <= 0) return;
+    k_route<true><<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
+}
+
+} // namespace raftk

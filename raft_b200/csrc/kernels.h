@@ -1,0 +1,163 @@
+// kernels.h — host-visible launchers of the raft_b200 CUDA kernels (internal; the public boundary
+// is include/raft_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nametable.cuh"
+
+namespace raftk {
+
+// device-side error codes (same numbering as raftgpu_status)
+enum { RAFTK_E_UNKNOWN_NAME = -2, RAFTK_E_DUP_NAME = -3, RAFTK_E_RANGE = -4, RAFTK_E_NEG_START = -5, RAFTK_E_HASH_COLLISION = -100 };
+
+struct ErrState {
+    long long index; // smallest offending record / read index (LLONG_MAX when clean)
+    int       code;
+    int       pad;
+};
+
+// ---------------------------------------------------------------- name table (nametable.cu)
+cudaError_t launch_name_build(NameTable* out_table_desc_host, void* slots, unsigned long long capacity, unsigned long long seed,
+                              const uint8_t* names, const int64_t* name_off, int64_t n, ErrState* err, cudaStream_t st);
+
+// ---------------------------------------------------------------- K1 (k1_paf.cu)
+struct PafTokArgs {
+    const uint8_t* text;
+    int64_t        nbytes;
+    int64_t        rec_base, rec_cap;
+    int32_t *      qid, *tid, *qs, *qe, *ts, *te;
+    uint8_t*       strand;
+    const int*     rec0;          // device int[7]: qid,tid,qs,qe,ts,te,present
+    int            first_is_local; // record index 0 of this context is the file's record 0
+    int            n_tiles;
+    uint64_t*      status;        // n_tiles words, zeroed
+    int*           ticket;        // zeroed
+    int*           sym_flag;
+    ErrState*      err;
+    int64_t*       n_records_out;
+    NameTable      names;
+};
+
+int         paf_tokenize_tiles(int64_t nbytes);
+cudaError_t launch_paf_tokenize(const PafTokArgs& a, cudaStream_t st);
+void        launch_paf_peek(const uint8_t* text, int64_t nbytes, const NameTable& nt, int* rec0, ErrState* err, cudaStream_t st);
+
+// ---------------------------------------------------------------- layout + K2 (k2_coverage.cu)
+// per owned read: slots = nb+1, repeat capacity, cut capacity  (int32 each)
+void launch_read_layout(const int64_t* seq_off_local, int64_t m, int reso, int p, int P, int l, int32_t* slots, int32_t* rep_cap,
+                        int32_t* cut_cap, cudaStream_t st);
+// exclusive scan int32[n] -> int64[n+1]; tmp_status must hold scan_tiles(n) uint64 (+1 int ticket after it), zeroed by the launcher
+int  scan_tiles_small(int64_t n);
+void launch_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, uint64_t* status, int* ticket, cudaStream_t st);
+// in-place inclusive scan of the int32 difference array
+int  scan_tiles_cov(int64_t n);
+void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, cudaStream_t st);
+
+struct ScatterArgs {
+    const int32_t *qid, *tid, *qs, *qe, *ts, *te;
+    int64_t        n_rec;
+    const int64_t* slot_off; // owned reads, m+1
+    int32_t*       diff;
+    int            reso;
+    int64_t        own_first, own_count;
+    const int*     sym_flag;
+    ErrState*      err;
+};
+void launch_scatter_records(const ScatterArgs& a, cudaStream_t st);
+// routed endpoints: int32 triples (global read id, start, end)
+void launch_scatter_endpoints(const int32_t* ep, int64_t n, const int64_t* slot_off, int32_t* diff, int reso, int64_t own_first,
+                              int64_t own_count, ErrState* err, cudaStream_t st);
+// multi-GPU routing
+void launch_route_count(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* counts_dev, cudaStream_t st);
+void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* cursors_dev, int32_t* sendbuf,
+                       cudaStream_t st);
+
+// ---------------------------------------------------------------- K3 (k3_repeat_cut.cu)
+struct RepeatCutArgs {
+    const int32_t* cov;      // scanned slots
+    const int64_t* slot_off; // m+1
+    const int64_t* seq_off;  // m+1 (lengths)
+    int64_t        m;
+    int            reso, H, p, P, f, l;
+    const int64_t* rep_cap_off; // m+1
+    const int64_t* cut_cap_off; // m+1
+    int2*          rep;         // capacity layout
+    int32_t*       rep_cnt;     // m
+    int32_t*       cuts;        // capacity layout
+    int32_t*       frag_cnt;    // m
+    unsigned long long* stats;  // [0]=sum cov, [1]=sum raw repeat len
+    int*           work_counter; // zeroed
+};
+void launch_repeat_cut(const RepeatCutArgs& a, cudaStream_t st);
+
+struct FragExpandArgs {
+    int64_t        m;
+    const int64_t* seq_off;     // local, m+1
+    const int64_t* name_off;    // global name offsets, indexed by global id
+    int64_t        own_first;
+    const int64_t* cut_cap_off;
+    const int32_t* cuts;
+    const int32_t* frag_cnt;
+    const int64_t* frag_base;   // m+1 (exclusive scan of frag_cnt)
+    int            v;
+    int64_t        read_num_base; // read= number of this context's first fragment minus 1
+    int32_t *      frag_read, *frag_a, *frag_b; // G
+    int32_t*       frag_size;   // G: bytes of the FASTA record
+    ErrState*      err;
+};
+void launch_frag_expand(const FragExpandArgs& a, cudaStream_t st);
+// compact repeats: rep_off = exclusive scan of rep_cnt; rep_out[2*k] pairs in read order; also text size per read line
+void launch_rep_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, int64_t m, int64_t own_first, int32_t* line_size,
+                      cudaStream_t st);
+void launch_rep_compact(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int64_t* rep_off, const int2* rep, int64_t m, int32_t* out,
+                        cudaStream_t st);
+
+// ---------------------------------------------------------------- K5 (k5_emit.cu)
+constexpr int COV_TILE_SLOTS = 1024;
+struct CovEmitArgs {
+    const int32_t* cov;      // scanned slots
+    const int64_t* slot_off; // m+1
+    int64_t        m, n_slots;
+    int64_t        own_first; // global id of local read 0
+    int            reso;
+    const int64_t* tile_off;  // n_tiles+1 (bytes), null for the sizing pass
+    int32_t*       tile_bytes; // sizing pass output
+    uint8_t*       dst;       // window buffer: byte (w0 + k) of the stream goes to dst[k]
+    int64_t        w0, w1;
+    int64_t        tile_first; // first tile of this launch
+};
+int  cov_tiles(int64_t n_slots);
+void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st);
+void launch_cov_emit(const CovEmitArgs& a, int64_t n_tiles_launch, cudaStream_t st);
+
+struct RepEmitArgs {
+    const int32_t* rep_cnt;
+    const int64_t* rep_cap_off;
+    const int2*    rep;
+    const int64_t* line_off; // m+1
+    int64_t        m, own_first;
+    uint8_t*       dst;
+    int64_t        w0, w1;
+    int64_t        read_first, read_last; // local read range to emit
+};
+void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st);
+
+constexpr int FASTA_TILE = 16384;
+struct FastaEmitArgs {
+    const int32_t *frag_read, *frag_a, *frag_b;
+    const int64_t* frag_off; // G+1 byte offsets of the records
+    int64_t        G;
+    const uint8_t* seq;      // local arena
+    const int64_t* seq_off;  // local m+1
+    const uint8_t* names;
+    const int64_t* name_off; // global
+    int64_t        own_first, read_num_base;
+    uint8_t*       dst;
+    int64_t        w0, w1;   // stream window; tile t covers [w0a + t*TILE, ...) with w0a = w0 rounded down to the tile grid of dst
+};
+void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st);
+
+void launch_digest(const uint8_t* buf, int64_t n, int64_t abs_off, unsigned long long* acc, cudaStream_t st);
+
+} // namespace raftk

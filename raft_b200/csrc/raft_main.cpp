@@ -1,0 +1,80 @@
+// raft_main.cpp — the `raft` command line on top of libraft_b200.so.
+// Same flags, defaults, quirks, log lines and exit codes as the reference's main.cpp:7-87; the work
+// itself is raftgpu_break_long_reads (the drop-in for break_long_reads, chop.hpp:331).
+#include <getopt.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "../../include/raft_b200.h"
+
+static void print_help(const raftgpu_params& p, const std::string& prefix)
+{ // main.cpp:7-19 (exit code 1 included)
+    std::cout << "Usage: raft [options] <input-reads.fa> <in.paf>\n";
+    std::cout << "  -r NUM     resolution of coverage " << p.reso << "\n";
+    std::cout << "  -e NUM     estimated coverage " << "\n";
+    std::cout << "  -m NUM     coverage multiplier " << p.cov_mul << "\n";
+    std::cout << "  -l NUM     read_length " << p.read_length << "\n";
+    std::cout << "  -v NUM     overlap_length " << p.overlap_length << "\n";
+    std::cout << "  -p NUM     repeat_length " << p.repeat_length << "\n";
+    std::cout << "  -f NUM     flanking_length " << p.flanking_length << "\n";
+    std::cout << "  -o FILE    prefix of output files " << prefix << "\n";
+    exit(1);
+}
+
+int main(int argc, char* argv[])
+{
+    raftgpu_params p;
+    raftgpu_default_params(&p);
+    std::string prefix = "raft"; // param.hpp:28
+    int         option;
+    while ((option = getopt(argc, argv, "r:e:m:l:i:p:f:v:o:")) != -1) {
+        switch (option) {
+        case 'r': p.reso = atoi(optarg); break;
+        case 'e': p.est_cov = atoi(optarg); break;
+        case 'm': p.cov_mul = std::stod(optarg); break;
+        case 'l': p.read_length = atoi(optarg); break;
+        case 'p': p.repeat_length = atoi(optarg); p.interval_length = atoi(optarg); break; // main.cpp:44-47
+        case 'f': p.flanking_length = atoi(optarg); break;
+        case 'v': p.overlap_length = atoi(optarg); // main.cpp:51-55: no break, -v also sets the prefix
+        /* fall through */
+        case 'o': prefix = optarg; break;
+        default: print_help(p, prefix); // includes -i, accepted by the optstring but unhandled (main.cpp:28,56-57)
+        }
+    }
+    if (argc < optind + 2) print_help(p, prefix);
+    if (p.est_cov <= 0) {
+        std::cout << "ERROR, main(), estimated coverage must be set properly\n";
+        print_help(p, prefix);
+    }
+    // param.hpp:33-43
+    std::cout << "INFO, printParams(), reso = " << p.reso << "\n";
+    std::cout << "INFO, printParams(), est_cov = " << p.est_cov << "\n";
+    std::cout << "INFO, printParams(), cov_mul = " << p.cov_mul << "\n";
+    std::cout << "INFO, printParams(), repeat_length = " << p.repeat_length << "\n";
+    std::cout << "INFO, printParams(), interval_length = " << p.interval_length << "\n";
+    std::cout << "INFO, printParams(), read_length = " << p.read_length << "\n";
+    std::cout << "INFO, printParams(), overlap_length = " << p.overlap_length << "\n";
+    std::cout << "INFO, printParams(), flanking_length = " << p.flanking_length << "\n";
+
+    auto t0 = std::chrono::system_clock::now();
+    std::cout << "INFO, main(), started timer\n";
+    std::cout.flush();
+
+    const char* dev_env = getenv("RAFT_B200_DEVICE");
+    int         st = raftgpu_break_long_reads(argv[optind], argv[optind + 1], &p, prefix.c_str(), dev_env ? atoi(dev_env) : 0, nullptr);
+    fflush(stdout);
+    if (st == RAFTGPU_E_IO) return 1; // chop.hpp:339-348 exit(1)
+    if (st != RAFTGPU_OK) return 2;   // inputs on which the reference crashes (segfault / SIGFPE / throw) or CUDA failure
+
+    std::chrono::duration<double> wct = std::chrono::system_clock::now() - t0;
+    std::cout << "INFO, main(), program completed after " << wct.count() << " seconds\n";
+    fprintf(stdout, "INFO, %s(), CMD:", __func__);
+    for (int i = 0; i < argc; ++i) fprintf(stdout, " %s", argv[i]);
+    std::cout << "\n";
+    return 0;
+}

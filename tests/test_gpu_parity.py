@@ -1,0 +1,172 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle and the committed
+reference outputs.  Everything here is bit-exact (integer / byte work)."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
+from oracle import oracle as O
+from raft_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = manifest()
+WHICH = {"coverage.txt": api.OUT_COVERAGE, "long_repeats.txt": api.OUT_LONG_REPEATS, "long_repeats.bed": api.OUT_BED,
+         "reads.fasta": api.OUT_READS_FASTA}
+
+
+def gpu_run(reads, paf, params, chunks=None):
+    ctx = api.Context(params)
+    ctx.set_reads(np.ascontiguousarray(reads.seq_off, np.int64), np.ascontiguousarray(reads.seq, np.uint8),
+                  np.ascontiguousarray(reads.name_off, np.int64), np.ascontiguousarray(reads.names, np.uint8))
+    if chunks is None:
+        ctx.ingest_paf(np.frombuffer(paf, np.uint8) if paf else np.zeros(0, np.uint8), len(paf), last=True)
+    else:
+        pos = 0
+        for k, c in enumerate(chunks):
+            piece = np.frombuffer(paf[pos:pos + c], np.uint8)
+            ctx.ingest_paf(piece, len(piece), last=(k == len(chunks) - 1))
+            pos += c
+        assert pos == len(paf)
+    return ctx, ctx.run()
+
+
+def compare_all(ctx, st, ref, real=True):
+    assert st.n_records == ref.n_rec
+    assert st.symmetric == ref.symmetric and st.high_cov == ref.high_cov and st.real_reads == ref.real_reads
+    for tab, name in ((api.TAB_QID, "qid"), (api.TAB_TID, "tid"), (api.TAB_QS, "qs"), (api.TAB_QE, "qe"),
+                      (api.TAB_TS, "ts"), (api.TAB_TE, "te"), (api.TAB_STRAND, "strand")):
+        np.testing.assert_array_equal(ctx.table(tab), getattr(ref, name), err_msg=name)
+    np.testing.assert_array_equal(ctx.table(api.TAB_BIN_OFF), ref.bin_off)
+    np.testing.assert_array_equal(ctx.table(api.TAB_COV), ref.cov)
+    np.testing.assert_array_equal(ctx.table(api.TAB_REP_OFF), ref.rep_off)
+    np.testing.assert_array_equal(ctx.table(api.TAB_REP).reshape(-1, 2), np.stack([ref.rep_s, ref.rep_e], 1))
+    np.testing.assert_array_equal(ctx.table(api.TAB_FRAG).reshape(-1, 3), np.stack([ref.frag_read, ref.frag_a, ref.frag_b], 1))
+    assert (st.total_cov, st.total_windows, st.total_repeat_len, st.total_read_len) == (
+        ref.total_cov, ref.total_windows, ref.total_repeat_len, ref.total_read_len)
+    assert ctx.fetch(api.OUT_COVERAGE) == ref.cov_txt
+    assert ctx.fetch(api.OUT_LONG_REPEATS) == ref.rep_txt
+    if real:
+        assert ctx.fetch(api.OUT_READS_FASTA) == ref.fasta
+        assert ctx.fetch(api.OUT_BED) == ref.bed_txt
+        for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta)):
+            assert ctx.digest(which) == O.digest(data)
+
+
+@pytest.mark.parametrize("entry", [e for e in CASES if e["name"] != "sim"], ids=lambda e: e["name"])
+def test_golden_through_c_abi(entry):
+    """Outputs equal the reference binary's committed outputs (tests/golden)."""
+    fa, paf = load_inputs(entry)
+    reads = O.parse_fasta(fa)
+    kw = args_to_kw(entry["args"])
+    ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
+    for suf in SUFS:
+        check_output(entry, suf, ctx.fetch(WHICH[suf]))
+    assert stdout_value(entry, "Symmetric overlaps") == f"INFO, Symmetric overlaps {st.symmetric} "
+    assert stdout_value(entry, "length of alignments") == f"INFO, length of alignments  {st.n_records}()"
+    assert stdout_value(entry, "high_cov") == f"high_cov {st.high_cov}"
+    compare_all(ctx, st, O.run(reads, paf, O.make_params(**kw)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg,scale,sym", [("C1", 0.3, True), ("C1", 0.3, False), ("C2", 0.0004, True), ("C2", 0.0004, False),
+                                           ("C4", 0.002, True), ("C4", 0.002, False), ("C5", 0.004, True), ("C5", 0.004, False)])
+def test_configs_vs_oracle(cfg, scale, sym):
+    ds = synth.make_dataset(cfg, scale, sym, seed=777)
+    p = api.AlgoParams.from_args(ds.args)
+    ctx, st = gpu_run(ds.reads, ds.paf, p)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    assert ref.status == 0
+    compare_all(ctx, st, ref)
+    ctx.close()
+
+
+def test_chunked_ingest_and_windowed_fetch():
+    ds = synth.make_dataset("C1", 0.1, False, seed=5)
+    p = api.AlgoParams.from_args(ds.args)
+    n = len(ds.paf)
+    # chunk boundaries in the middle of lines, a 1-byte chunk, and an empty final chunk
+    chunks = [1000, 1, 77777, n // 3, 0]
+    chunks.append(n - sum(chunks))
+    chunks.append(0)
+    ctx, st = gpu_run(ds.reads, ds.paf, p, chunks=chunks)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    compare_all(ctx, st, ref)
+    # windows at odd offsets / sizes reproduce the same bytes
+    for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta)):
+        total = ctx.output_size(which)
+        assert total == len(data)
+        for off, ln in ((0, 1), (1, 17), (total // 2 + 3, 100001), (total - 5, 5), (12345, 65536 + 7)):
+            ln = min(ln, total - off)
+            assert ctx.fetch(which, off, ln) == data[off:off + ln], (which, off, ln)
+    ctx.close()
+
+
+def test_device_resident_inputs_and_outputs():
+    torch = pytest.importorskip("torch")
+    ds = synth.make_dataset("C2", 0.0003, True, seed=9)
+    p = api.AlgoParams.from_args(ds.args)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    seq_off, seq, name_off, names = t(ds.reads.seq_off), t(ds.reads.seq), t(ds.reads.name_off), t(ds.reads.names)
+    paf = t(np.frombuffer(ds.paf, np.uint8))
+    torch.cuda.synchronize()
+    ctx = api.Context(p)
+    ctx.set_reads(seq_off, seq, name_off, names)
+    ctx.ingest_paf(paf, paf.numel(), last=True)
+    st = ctx.run()
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta)):
+        total = ctx.output_size(which)
+        out = torch.empty(total + 3, dtype=torch.uint8, device=dev)
+        ctx.fetch_into(which, 0, out[3:], total)  # deliberately misaligned destination
+        torch.cuda.synchronize()
+        assert out[3:].cpu().numpy().tobytes() == data
+    assert st.n_records == ref.n_rec
+    ctx.close()
+
+
+def test_error_domain_matches_oracle():
+    fa = b">a\nACGTACGTAC\n>b\nACGTACGTACGG\n"
+    reads = O.parse_fasta(fa)
+    line = lambda *f: b"\t".join(str(x).encode() for x in f) + b"\n"
+    ok = line("a", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255)
+    cases = [(line("zz", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -2),
+             (ok + line("a", 10, 0, 10, "+", "nope", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -2),
+             (line("a", 10, 0, 500, "+", "b", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -4),
+             (ok, dict(est_cov=1, repeat_length=5, read_length=5, overlap_length=50), -5)]
+    for paf, kw, want in cases:
+        assert O.run(reads, paf, O.make_params(**kw)).status == want
+        with pytest.raises(api.RaftError) as ei:
+            gpu_run(reads, paf, api.AlgoParams(**kw))
+        assert ei.value.status == want
+    with pytest.raises(api.RaftError) as ei:
+        api.Context(api.AlgoParams(est_cov=1, read_length=50, repeat_length=100))
+    assert ei.value.status == -1
+    dup = O.parse_fasta(b">a\nAC\n>a\nGT\n")
+    with pytest.raises(api.RaftError) as ei:
+        gpu_run(dup, b"", api.AlgoParams(est_cov=1))
+    assert ei.value.status == -3
+
+
+def test_cli_binary_against_golden():
+    """The `raft` executable (C++ host over the C ABI): same files and stdout lines as the reference."""
+    exe = os.path.join(ROOT, "raft_b200", "raft")
+    assert os.path.exists(exe), "run make"
+    for entry in CASES:
+        if entry["name"] in ("sim",):
+            continue
+        fa, paf = load_inputs(entry)
+        with tempfile.TemporaryDirectory() as d:
+            open(os.path.join(d, "r.fa"), "wb").write(fa)
+            open(os.path.join(d, "o.paf"), "wb").write(paf)
+            r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "out"), os.path.join(d, "r.fa"), os.path.join(d, "o.paf")],
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+            assert r.returncode == 0, r.stdout.decode()
+            for suf in SUFS:
+                check_output(entry, suf, open(os.path.join(d, "out." + suf), "rb").read())
+            got = [l for l in r.stdout.decode().splitlines() if not l.startswith("INFO, main(), program completed") and "CMD:" not in l]
+            assert got == entry["stdout"], entry["name"]
