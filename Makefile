@@ -9,7 +9,7 @@ CU        := nametable k1_paf k2_coverage k3_repeat_cut k5_emit api
 OBJS      := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/host_io.o
 LIB       := raft_b200/libraft_b200.so
 
-all: $(LIB) raft_b200/raft oracle
+all: $(LIB) raft_b200/raft raft_b200/libraft_synth.so oracle
 
 $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh include/raft_b200.h
 	@mkdir -p $(OBJ)
@@ -22,6 +22,9 @@ $(OBJ)/host_io.o: $(SRC)/host_io.cpp include/raft_b200.h
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz
 
+raft_b200/libraft_synth.so: $(SRC)/synth_gen.cu $(SRC)/common.cuh
+	$(NVCC) $(NVFLAGS) -shared $< -o $@
+
 raft_b200/raft: $(SRC)/raft_main.cpp $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -Lraft_b200 -lraft_b200 -Wl,-rpath,'$$ORIGIN'
 
@@ -29,6 +32,6 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(OBJ) $(LIB) raft_b200/raft
+	rm -rf $(OBJ) $(LIB) raft_b200/raft raft_b200/libraft_synth.so
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

@@ -87,6 +87,13 @@ typedef struct {
     float    ms_tokenize, ms_scatter, ms_scan, ms_repeat_cut, ms_layout, ms_total;
     int32_t  kernel_launches;  /* kernels launched by the library since raftgpu_reset */
     int32_t  reserved;
+    /* emitters (raftgpu_fetch / raftgpu_digest): accumulated device time of the emit kernels per stream,
+     * CUDA events on the launching stream, and how many emit kernels / stream bytes that covers */
+    float    ms_emit[4];
+    int32_t  emit_launches[4];
+    uint64_t emit_bytes[4];
+    float    ms_set_reads;     /* device time of raftgpu_set_reads (copies, layout scans, name table) */
+    int32_t  reserved2;
 } raftgpu_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -120,6 +127,8 @@ int raftgpu_ingest_paf(raftgpu_ctx *ctx, const uint8_t *text, size_t nbytes, int
 /* ---- a3-a5: coverage, repeats, cut points.  Replaces profileCoverage + repeat_annotate
  * (repeat.hpp:28-204, minus file writing) and the boundary arithmetic of break_reads (chop.hpp:198-323). */
 int raftgpu_run(raftgpu_ctx *ctx, raftgpu_stats *stats);
+/* Current counters (stage times, emit times, kernel launches) without running anything. */
+int raftgpu_get_stats(raftgpu_ctx *ctx, raftgpu_stats *stats);
 
 /* ---- outputs: the bytes of prefix.coverage.txt / .long_repeats.txt / .long_repeats.bed /
  * .reads.fasta (repeat.hpp:105-108,180-203; chop.hpp:250-322), materialised on the device window

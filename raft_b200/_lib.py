@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libraft_b200.so")
 SYMBOLS = [
     "raftgpu_default_params", "raftgpu_create", "raftgpu_destroy", "raftgpu_reset", "raftgpu_strerror",
     "raftgpu_last_error", "raftgpu_error_index", "raftgpu_set_reads", "raftgpu_load_fasta", "raftgpu_free_host",
-    "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_digest",
+    "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_digest",
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
     "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
@@ -31,7 +31,9 @@ class Stats(C.Structure):
                 ("n_repeats", C.c_int64), ("n_fragments", C.c_int64), ("out_bytes", C.c_uint64 * 4),
                 ("ms_tokenize", C.c_float), ("ms_scatter", C.c_float), ("ms_scan", C.c_float),
                 ("ms_repeat_cut", C.c_float), ("ms_layout", C.c_float), ("ms_total", C.c_float),
-                ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("reserved", C.c_int32),
+                ("ms_emit", C.c_float * 4), ("emit_launches", C.c_int32 * 4), ("emit_bytes", C.c_uint64 * 4),
+                ("ms_set_reads", C.c_float), ("reserved2", C.c_int32)]
 
 
 _lib = None
@@ -60,6 +62,7 @@ def lib():
         "raftgpu_free_host": (None, [vp]),
         "raftgpu_ingest_paf": (C.c_int, [vp, vp, sz, C.c_int]),
         "raftgpu_run": (C.c_int, [vp, PS]),
+        "raftgpu_get_stats": (C.c_int, [vp, PS]),
         "raftgpu_output_size": (C.c_int, [vp, C.c_int, C.POINTER(u64)]),
         "raftgpu_fetch": (C.c_int, [vp, C.c_int, u64, vp, sz]),
         "raftgpu_digest": (C.c_int, [vp, C.c_int, C.POINTER(u64)]),

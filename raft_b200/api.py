@@ -129,6 +129,11 @@ class Context:
         self._ck(self.L.raftgpu_run(self._h, C.byref(s)))
         return s
 
+    def stats(self):
+        s = _lib.Stats()
+        self._ck(self.L.raftgpu_get_stats(self._h, C.byref(s)))
+        return s
+
     def finalize(self):
         s = _lib.Stats()
         self._ck(self.L.raftgpu_finalize(self._h, C.byref(s)))

@@ -104,6 +104,9 @@ struct raftgpu_ctx {
     DevBuf  b_stage[2];
     cudaEvent_t ev[8]{};
     cudaEvent_t ev_stage[2]{};
+    cudaEvent_t ev_emit[2]{};
+    bool        emit_pending = false;
+    int         emit_pending_which = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -182,6 +185,7 @@ int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) return bail();
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
+    for (auto& e : ctx->ev_emit) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     if (ctx->b_misc.ensure(sizeof(Misc)) != cudaSuccess) return bail();
     *out = ctx;
     return raftgpu_reset(ctx);
@@ -194,6 +198,7 @@ int raftgpu_destroy(raftgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_emit) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
     delete ctx;
     return RAFTGPU_OK;
@@ -212,6 +217,7 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
+    ctx->emit_pending = false;
     return RAFTGPU_OK;
 }
 
@@ -312,6 +318,7 @@ extern "C" int raftgpu_set_reads(raftgpu_ctx* ctx, int64_t n, const int64_t* seq
     CK(cudaSetDevice(ctx->device));
     int st = raftgpu_reset(ctx);
     if (st) return st;
+    cudaEventRecord(ctx->ev[0], ctx->st);
     int64_t name_bytes = 0, seq_bytes = 0;
     CK(cudaMemcpy(&name_bytes, name_off + n, 8, cudaMemcpyDefault));
     CK(cudaMemcpy(&seq_bytes, seq_off + n, 8, cudaMemcpyDefault));
@@ -324,7 +331,10 @@ extern "C" int raftgpu_set_reads(raftgpu_ctx* ctx, int64_t n, const int64_t* seq
     else ctx->d_seq = nullptr;
     std::string first;
     if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
-    return build_layout_and_names(ctx, first);
+    st = build_layout_and_names(ctx, first);
+    cudaEventRecord(ctx->ev[1], ctx->st);
+    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_set_reads, ctx->ev[0], ctx->ev[1]);
+    return st;
 }
 
 extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int64_t* lengths, const int64_t* name_off, const uint8_t* names,
@@ -750,9 +760,34 @@ extern "C" int raftgpu_run(raftgpu_ctx* ctx, raftgpu_stats* out)
 
 // ------------------------------------------------------------------------------------------------ outputs
 // materialise stream bytes [w0, w1) of `which` at device address d (d[k] = stream byte w0+k)
+static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st);
 static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st)
 {
     if (w1 <= w0) return RAFTGPU_OK;
+    // the previous window's events have completed by now or are waited for here (cheap: same stream)
+    if (ctx->emit_pending) {
+        cudaEventSynchronize(ctx->ev_emit[1]);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_emit[0], ctx->ev_emit[1]) == cudaSuccess) ctx->stats.ms_emit[ctx->emit_pending_which] += ms;
+        ctx->emit_pending = false;
+    }
+    cudaEventRecord(ctx->ev_emit[0], st);
+    int rc = emit_window_impl(ctx, which, w0, w1, d, st);
+    cudaEventRecord(ctx->ev_emit[1], st);
+    ctx->emit_pending = true; ctx->emit_pending_which = which;
+    ctx->stats.emit_launches[which]++; ctx->stats.emit_bytes[which] += (uint64_t)(w1 - w0);
+    return rc;
+}
+static void flush_emit_timer(raftgpu_ctx* ctx)
+{
+    if (!ctx->emit_pending) return;
+    cudaEventSynchronize(ctx->ev_emit[1]);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_emit[0], ctx->ev_emit[1]) == cudaSuccess) ctx->stats.ms_emit[ctx->emit_pending_which] += ms;
+    ctx->emit_pending = false;
+}
+static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st)
+{
     const int64_t m = ctx->m;
     if (which == RAFTGPU_OUT_COVERAGE) {
         const auto& off = ctx->h_cov_tile_off;
@@ -788,6 +823,15 @@ static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint
     return RAFTGPU_OK;
 }
 
+extern "C" int raftgpu_get_stats(raftgpu_ctx* ctx, raftgpu_stats* out)
+{
+    if (!ctx || !out) return RAFTGPU_E_ARG;
+    flush_emit_timer(ctx);
+    ctx->stats.kernel_launches = ctx->launches;
+    *out = ctx->stats;
+    return RAFTGPU_OK;
+}
+
 extern "C" int raftgpu_output_size(raftgpu_ctx* ctx, int which, uint64_t* nbytes)
 {
     if (!ctx || !nbytes || which < 0 || which > 3) return RAFTGPU_E_ARG;
@@ -802,7 +846,7 @@ extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t*
     if (!ctx || which < 0 || which > 3 || (!dst && n)) return RAFTGPU_E_ARG;
     int st = layout_outputs(ctx);
     if (st) return st;
-    if (off + n > ctx->stats.out_bytes[which]) return RAFTGPU_E_ARG;
+    if (off > ctx->stats.out_bytes[which] || n > ctx->stats.out_bytes[which] - off) return RAFTGPU_E_ARG;
     if (!n) return RAFTGPU_OK;
     CK(cudaSetDevice(ctx->device));
     if (is_device_ptr(dst)) {

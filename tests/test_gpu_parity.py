@@ -99,9 +99,11 @@ def test_chunked_ingest_and_windowed_fetch():
     for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta)):
         total = ctx.output_size(which)
         assert total == len(data)
-        for off, ln in ((0, 1), (1, 17), (total // 2 + 3, 100001), (total - 5, 5), (12345, 65536 + 7)):
+        for off, ln in ((0, 1), (1, 17), (total // 2 + 3, 100001), (total - 5, 5), (min(12345, total // 3), 65536 + 7)):
             ln = min(ln, total - off)
             assert ctx.fetch(which, off, ln) == data[off:off + ln], (which, off, ln)
+        with pytest.raises(api.RaftError):
+            ctx.fetch(which, total - 1, 2)
     ctx.close()
 
 
@@ -137,7 +139,7 @@ def test_error_domain_matches_oracle():
     cases = [(line("zz", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -2),
              (ok + line("a", 10, 0, 10, "+", "nope", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -2),
              (line("a", 10, 0, 500, "+", "b", 12, 0, 10, 10, 10, 255), dict(est_cov=1), -4),
-             (ok, dict(est_cov=1, repeat_length=5, read_length=5, overlap_length=50), -5)]
+             (ok, dict(est_cov=5, repeat_length=5, read_length=5, overlap_length=50), -5)]
     for paf, kw, want in cases:
         assert O.run(reads, paf, O.make_params(**kw)).status == want
         with pytest.raises(api.RaftError) as ei:
