@@ -97,7 +97,7 @@ struct raftgpu_ctx {
     DevBuf  b_cov; bool diff_zeroed = false, finalized = false, sized = false;
     DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
-    DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off;
+    DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
     std::vector<int64_t> h_cov_tile_off, h_rep_line_off;
     int64_t G = 0, n_repeats = 0, read_num_base = 0;
     raftgpu_stats stats{};
@@ -710,9 +710,13 @@ static int layout_outputs(raftgpu_ctx* ctx)
     // coverage.txt tiles
     const int T = cov_tiles(ctx->n_slots);
     CK(ctx->b_cov_tile_bytes.ensure(sizeof(int32_t) * (size_t)(T + 1))); CK(ctx->b_cov_tile_off.ensure(sizeof(int64_t) * (size_t)(T + 1)));
+    CK(ctx->b_cov_tile_read.ensure(sizeof(int32_t) * (size_t)(T + 2)));
+    launch_cov_tile_index(ctx->b_slot_off.as<int64_t>(), m, ctx->n_slots, ctx->b_cov_tile_read.as<int32_t>(), ctx->st);
+    CKL();
     CovEmitArgs ca{};
     ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
     ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_bytes = ctx->b_cov_tile_bytes.as<int32_t>(); ca.tile_first = 0;
+    ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
     launch_cov_sizes(ca, ctx->st);
     CKL();
     launch_scan_i32_to_i64(ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_off.as<int64_t>(), T, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
@@ -730,6 +734,16 @@ static int layout_outputs(raftgpu_ctx* ctx)
     s.out_bytes[RAFTGPU_OUT_LONG_REPEATS] = (uint64_t)ctx->h_rep_line_off[m];
     s.out_bytes[RAFTGPU_OUT_BED] = 0; // real reads: the file is created empty (repeat.hpp:87,187)
     s.out_bytes[RAFTGPU_OUT_READS_FASTA] = (uint64_t)fasta_bytes;
+    // record containing the first byte of every 16 KiB tile of reads.fasta
+    CK(ctx->b_fasta_tile_frag.ensure(sizeof(int32_t) * (size_t)(fasta_bytes / FASTA_TILE + 2)));
+    launch_fasta_tile_index(ctx->b_frag_off.as<int64_t>(), G, ctx->b_fasta_tile_frag.as<int32_t>(), ctx->st);
+    CKL();
+    CK(ctx->b_frag_desc.ensure(sizeof(FragDesc) * (size_t)(G + 1)));
+    launch_frag_desc(ctx->b_frag_read.as<int32_t>(), ctx->b_frag_a.as<int32_t>(), ctx->b_frag_b.as<int32_t>(), ctx->b_frag_size.as<int32_t>(),
+                     ctx->b_frag_off.as<int64_t>(), ctx->d_seq_off, G, ctx->b_frag_desc.as<FragDesc>(), ctx->st);
+    CKL();
+    cudaEventRecord(ctx->ev[7], ctx->st);
+    CK(cudaStreamSynchronize(ctx->st));
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); s.ms_layout = ms;
     s.kernel_launches = ctx->launches;
     ctx->sized = true;
@@ -796,7 +810,7 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         CovEmitArgs ca{};
         ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
         ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
-        ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0;
+        ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0; ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
         launch_cov_emit(ca, t1 - t0, st);
         CKL();
     } else if (which == RAFTGPU_OUT_LONG_REPEATS) {
@@ -813,10 +827,11 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         if (!ctx->have_seq) FAIL(RAFTGPU_E_STATE, "reads.fasta requested but no sequence bytes were given");
         if (!ctx->real_reads) FAIL(RAFTGPU_E_UNSUPPORTED, "simulated-read headers (chop.hpp:252-258,293-310) are not emitted by the device path");
         FastaEmitArgs fa{};
-        fa.frag_read = ctx->b_frag_read.as<int32_t>(); fa.frag_a = ctx->b_frag_a.as<int32_t>(); fa.frag_b = ctx->b_frag_b.as<int32_t>();
-        fa.frag_off = ctx->b_frag_off.as<int64_t>(); fa.G = ctx->G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
+        fa.desc = ctx->b_frag_desc.as<FragDesc>(); fa.G = ctx->G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
         fa.names = ctx->d_names; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first; fa.read_num_base = ctx->read_num_base;
-        fa.dst = d; fa.w0 = w0; fa.w1 = w1;
+        fa.dst = d; fa.w0 = w0; fa.w1 = w1; fa.tile_frag = ctx->b_fasta_tile_frag.as<int32_t>();
+        // owned arenas are padded by 32 bytes; borrowed ones are only trusted up to their last whole 16-byte block
+        fa.seq_safe_end = (ctx->d_seq == ctx->b_seq.as<uint8_t>()) ? ((ctx->total_read_len + 31) & ~(int64_t)15) : (ctx->total_read_len & ~(int64_t)15);
         launch_fasta_emit(fa, st);
         CKL();
     }

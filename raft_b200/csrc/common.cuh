@@ -110,6 +110,24 @@ __device__ __forceinline__ uint64_t lookback_block(uint64_t* status, int tile, u
     return *bcast;
 }
 
+// Split form: publish the aggregate early, wait for the prefix later (work can sit in between).
+__device__ __forceinline__ void lookback_publish(uint64_t* status, int tile, uint64_t agg)
+{ // one thread
+    st_relaxed_u64(status + tile, (tile == 0 ? LB_PREFIX : LB_AGG) | (agg & LB_MASK));
+}
+__device__ __forceinline__ uint64_t lookback_wait(uint64_t* status, int tile, uint64_t agg, uint64_t* bcast)
+{ // all threads; contains __syncthreads()
+    if (warp_id() == 0) {
+        uint64_t ex = (tile == 0) ? 0ull : lookback_exclusive(status, tile);
+        if (lane_id() == 0) {
+            if (tile != 0) st_relaxed_u64(status + tile, LB_PREFIX | ((ex + agg) & LB_MASK));
+            *bcast = ex;
+        }
+    }
+    __syncthreads();
+    return *bcast;
+}
+
 __device__ __forceinline__ int64_t lb_signed(uint64_t v)
 { // sign-extend a 62-bit two's complement value
     return (int64_t)(v << 2) >> 2;

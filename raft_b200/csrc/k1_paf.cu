@@ -1,11 +1,16 @@
 // k1_paf.cu — K1: PAF tokenizer + id decode + symmetric-overlap predicate.
 //
 // Replaces paf_read/paf_parse (paf.hpp:50-99, line reader kseq.h:107-193) and the per-record part
-// of create_pileup (chop.hpp:147-187): the whole text sits in HBM, each CTA stages one 16 KiB tile
-// (+ overhang) into shared memory with a 1-D TMA bulk copy, finds newline and tab positions with
-// SWAR byte compares + popc + warp-shuffle scans, decides record validity (>= 10 fields,
-// paf.hpp:84) from cumulative tab counts, obtains its first record index with a decoupled
-// look-back over tiles, then decodes one line per thread into SoA int32 columns.
+// of create_pileup (chop.hpp:147-187).  The whole text sits in HBM; each CTA stages one 16 KiB tile
+// (+ 1 KiB overhang) into shared memory with a 1-D TMA bulk copy and turns it into three bit masks
+// (newline, tab, start-of-non-empty-line) with SWAR byte compares.  Everything per line is then
+// derived from the masks with popc / ffs: validity (>= 9 tabs before the line's newline,
+// paf.hpp:84) by popcounts, the tile's record count by a block scan, its first record index by a
+// decoupled look-back over tiles, the j-th valid line by select on the mask, and the nine field
+// boundaries by ffs hops over the tab mask.  Fields are decoded straight from shared memory:
+// names are hashed four bytes per step (funnel-shifted unaligned words), numbers by a digit loop.
+// Lines that run past the staged bytes (e.g. kilobyte cg:Z: CIGAR tags) take a byte-wise path
+// that reads global memory.
 //
 // Semantics kept from the reference:
 //  * a record is a line with >= 9 tabs; shorter / blank lines are skipped (paf.hpp:84-85,96-98);
@@ -22,26 +27,23 @@
 namespace raftk {
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_TILE = 16384;             // bytes of text whose newlines a CTA owns
 constexpr int K1_OVER = 1024;              // staged overhang: lines starting near the tile end
 constexpr int K1_STAGE = K1_TILE + K1_OVER;
-constexpr int K1_MAXLINES = K1_TILE / 2 + 1; // non-empty lines that can start in a tile (+1: file start)
-constexpr int K1_GROUPS_PER_WARP = K1_TILE / 16 / K1_WARPS; // 128 16-byte groups per warp
-constexpr int K1_ROUNDS = K1_GROUPS_PER_WARP / 32;          // 4
+constexpr int K1_WORDS = K1_STAGE / 32;    // 544 mask words over the staged bytes
+constexpr int K1_TWORDS = K1_TILE / 32;    // 512: line starts live in bits [0, TILE] -> words [0, 512]
 
 struct __align__(16) K1Smem {
-    uint8_t            text[K1_STAGE];
-    uint16_t           ls[K1_MAXLINES + 7]; // line start, tile relative (1..TILE; 0 only for file start)
-    uint16_t           lt[K1_MAXLINES + 7]; // cumulative tabs in [tile start, line start); later: record rank
-    uint64_t           bar;
-    uint64_t           bcast;
-    int                scan_ws[34];
-    int                wcnt_nl[K1_WARPS + 1];
-    int                wcnt_tab[K1_WARPS + 1];
-    int                tile;
-    int                last_line_tabs;
-    int                last_nl; // tile-relative position of the last newline byte in the tile, -1 if none
+    uint8_t  text[K1_STAGE + 16];
+    unsigned nl[K1_WORDS];    // byte is '\n'
+    unsigned tab[K1_WORDS];   // byte is '\t'
+    unsigned ls[K1_WORDS];    // a non-empty line owned by this tile starts at this byte
+    unsigned valid[K1_WORDS]; // ... and it is a record (>= 9 tabs)
+    uint16_t vpre[K1_WORDS + 2]; // records before word w
+    uint64_t bar;
+    uint64_t bcast;
+    int      scan_ws[34];
+    int      tile;
 };
 
 // bit k set iff byte k of the 16-byte group equals c
@@ -156,15 +158,102 @@ __device__ __forceinline__ void report_error(ErrState* err, int code, long long 
     if (index <= old) err->code = code;
 }
 
+// first set bit of mask m at position >= from (bit index over K1_WORDS words), or K1_STAGE
+__device__ __forceinline__ int next_bit(const unsigned* m, int from)
+{
+    if (from >= K1_STAGE) return K1_STAGE;
+    int      w = from >> 5;
+    unsigned x = m[w] & (0xFFFFFFFFu << (from & 31));
+    while (!x) { if (++w >= K1_WORDS) return K1_STAGE; x = m[w]; }
+    return (w << 5) + __ffs(x) - 1;
+}
+// number of set bits of m in [from, to)
+__device__ __forceinline__ int count_bits(const unsigned* m, int from, int to)
+{
+    if (to <= from) return 0;
+    int      w0 = from >> 5, w1 = (to - 1) >> 5;
+    unsigned first = 0xFFFFFFFFu << (from & 31), last = 0xFFFFFFFFu >> (31 - ((to - 1) & 31));
+    if (w0 == w1) return __popc(m[w0] & first & last);
+    int c = __popc(m[w0] & first) + __popc(m[w1] & last);
+    for (int w = w0 + 1; w < w1; w++) c += __popc(m[w]);
+    return c;
+}
+
+// strtol(base 10) -> uint32_t -> int over staged bytes [a, b)
+__device__ __noinline__ int parse_num_generic(const uint8_t* s, int a, int b)
+{
+    NumState num;
+    num.reset();
+    for (int i = a; i < b; i++) { num.add(s[i]); if (num.st == 3) break; }
+    return num.value();
+}
+// fast path: 1..9 plain digits filling the whole field
+__device__ __forceinline__ int parse_num_smem(const uint8_t* s, int a, int b)
+{
+    unsigned acc = 0;
+    int      i = a;
+    for (; i < b; i++) { unsigned d = (unsigned)s[i] - '0'; if (d > 9u) break; acc = acc * 10u + d; }
+    if (i == b && b > a && b - a <= 9) return (int)acc;
+    return parse_num_generic(s, a, b);
+}
+
+// hash of staged bytes [a, b): same value as NameHasher fed byte by byte
+__device__ __forceinline__ unsigned long long hash_name_smem(const unsigned* sw, int a, int b, unsigned long long seed)
+{
+    unsigned long long h = seed ^ 0x9E3779B97F4A7C15ull;
+    const int          n = b - a;
+    int                wi = a >> 2;
+    const unsigned     sh = (unsigned)(a & 3) * 8u;
+    unsigned           lo = sw[wi];
+    int                k = 0;
+    for (; k + 4 <= n; k += 4) {
+        unsigned hi = sw[++wi];
+        unsigned w = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+    }
+    const int rem = n - k;
+    if (rem) {
+        unsigned hi = sw[wi + 1];
+        unsigned w = __funnelshift_r(lo, hi, sh) & ((1u << (8 * rem)) - 1u);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+    }
+    unsigned long long r = mix64(h ^ ((unsigned long long)(unsigned)n << 32));
+    return r ? r : 1ull;
+}
+
+// position of the j-th set bit of a mask given its per-word exclusive prefix counts (pre has K1_TWORDS+2 entries)
+__device__ __forceinline__ int select_bit(const unsigned* m, const uint16_t* pre, int j)
+{
+    int lo = 0, hi = K1_TWORDS + 1;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)pre[mid] <= j) lo = mid; else hi = mid; }
+    unsigned v = m[lo];
+    for (int k = j - (int)pre[lo]; k > 0; k--) v &= v - 1;
+    return (lo << 5) + __ffs(v) - 1;
+}
+
+// exclusive prefix of popc over mask words [0, K1_TWORDS] -> pre[0..K1_TWORDS+1]; returns the total.  Block-wide.
+__device__ __forceinline__ int mask_prefix(const unsigned* m, uint16_t* pre, int* scan_ws)
+{
+    const int tid = threadIdx.x;
+    const int wlo = tid * 2, whi = (tid == K1_THREADS - 1) ? K1_TWORDS + 1 : wlo + 2;
+    int       mine = 0;
+    for (int w = wlo; w < whi; w++) mine += __popc(m[w]);
+    int tot;
+    int run = block_exclusive_sum<int, K1_THREADS>(mine, scan_ws, &tot);
+    for (int w = wlo; w < whi; w++) { pre[w] = (uint16_t)run; run += __popc(m[w]); }
+    if (tid == K1_THREADS - 1) pre[K1_TWORDS + 1] = (uint16_t)run;
+    return tot;
+}
+
 __global__ void __launch_bounds__(K1_THREADS) k_paf_tokenize(PafTokArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const int tid = threadIdx.x, lane = lane_id();
 
     if (tid == 0) {
         s.tile = atomicAdd(a.ticket, 1);
-        s.last_nl = -1;
         mbar_init(&s.bar, 1);
     }
     __syncthreads();
@@ -179,121 +268,114 @@ __global__ void __launch_bounds__(K1_THREADS) k_paf_tokenize(PafTokArgs a)
         mbar_expect_tx(&s.bar, (uint32_t)bulk);
         tma_load_1d(s.text, a.text + t0, (uint32_t)bulk, &s.bar);
     }
-    for (int j = bulk + tid; j < K1_STAGE; j += K1_THREADS) s.text[j] = (j < want) ? a.text[t0 + j] : (uint8_t)'\n';
+    for (int j = bulk + tid; j < K1_STAGE + 16; j += K1_THREADS) s.text[j] = (j < want) ? a.text[t0 + j] : (uint8_t)'\n';
     if (bulk > 0) mbar_wait(&s.bar, 0);
     __syncthreads();
 
-    // ---- pass 1: per-warp newline (line-start) and tab totals over its 2 KiB
+    // ---- newline / tab masks: one 16-byte group per lane, two lanes make one 32-bit word
     const uint4* t16 = reinterpret_cast<const uint4*>(s.text);
-    unsigned     m_nl[K1_ROUNDS], m_tab[K1_ROUNDS];
-    int          c_nl = 0, c_tab = 0, my_last_nl = -1;
-#pragma unroll
-    for (int r = 0; r < K1_ROUNDS; r++) {
-        int      g = warp * K1_GROUPS_PER_WARP + r * 32 + lane;
+    for (int g = tid; g < K1_STAGE / 16; g += K1_THREADS) { // 1088 groups; the last round is two full warps
         uint4    v = t16[g];
-        unsigned nl = eq_mask16(v, 0x0A0A0A0Au);
-        if (nl) my_last_nl = g * 16 + (31 - __clz(nl));
-        unsigned nxt = (nl >> 1) | ((s.text[g * 16 + 16] == '\n') ? 0x8000u : 0u);
-        m_nl[r] = nl & ~nxt;                 // newline followed by a non-newline byte: a non-empty line starts
-        m_tab[r] = eq_mask16(v, 0x09090909u);
-        c_nl += __popc(m_nl[r]); c_tab += __popc(m_tab[r]);
-    }
-    {
-        int wn = warp_sum(c_nl), wt = warp_sum(c_tab);
-        int wl = my_last_nl;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) wl = max(wl, __shfl_xor_sync(FULL, wl, d));
-        if (lane == 0) { s.wcnt_nl[warp] = wn; s.wcnt_tab[warp] = wt; if (wl >= 0) atomicMax(&s.last_nl, wl); }
+        unsigned mn = eq_mask16(v, 0x0A0A0A0Au), mt = eq_mask16(v, 0x09090909u);
+        unsigned pn = __shfl_down_sync(FULL, mn, 1), pt = __shfl_down_sync(FULL, mt, 1);
+        if (!(lane & 1)) { s.nl[g >> 1] = mn | (pn << 16); s.tab[g >> 1] = mt | (pt << 16); }
     }
     __syncthreads();
-    if (tid == 0) {
-        int an = (tile == 0) ? 1 : 0, at = 0; // the file's first byte starts a line (no preceding newline)
-        for (int w = 0; w < K1_WARPS; w++) { int n = s.wcnt_nl[w], t = s.wcnt_tab[w]; s.wcnt_nl[w] = an; s.wcnt_tab[w] = at; an += n; at += t; }
-        s.wcnt_nl[K1_WARPS] = an; s.wcnt_tab[K1_WARPS] = at;
-        if (tile == 0) { s.ls[0] = 0; s.lt[0] = 0; }
-    }
-    __syncthreads();
-    // ---- pass 2: write (line start, cumulative tabs) in text order
-    {
-        int bn = s.wcnt_nl[warp], bt = s.wcnt_tab[warp];
-#pragma unroll
-        for (int r = 0; r < K1_ROUNDS; r++) {
-            int g = warp * K1_GROUPS_PER_WARP + r * 32 + lane;
-            int cn = __popc(m_nl[r]), ct = __popc(m_tab[r]);
-            int in_ = warp_inclusive_sum(cn), it = warp_inclusive_sum(ct);
-            int on = bn + in_ - cn, ot = bt + it - ct;
-            unsigned m = m_nl[r];
-            while (m) {
-                int k = __ffs(m) - 1; m &= m - 1;
-                s.ls[on] = (uint16_t)(g * 16 + k + 1);
-                s.lt[on] = (uint16_t)(ot + __popc(m_tab[r] & ((2u << k) - 1u)));
-                on++;
-            }
-            bn += __shfl_sync(FULL, in_, 31); bt += __shfl_sync(FULL, it, 31);
+    // ---- line starts: byte p starts a non-empty line iff byte p-1 is '\n' (owned: p-1 inside the tile) and byte p is not
+    for (int w = tid; w < K1_WORDS; w += K1_THREADS) {
+        unsigned m = 0;
+        if (w <= K1_TWORDS) {
+            unsigned prev = w ? (s.nl[w - 1] >> 31) : ((tile == 0) ? 1u : 0u); // the file's first byte starts a line
+            m = ((s.nl[w] << 1) | prev) & ~s.nl[w];
+            if (w == K1_TWORDS) m &= 1u;
         }
+        s.ls[w] = m;
+        s.valid[w] = 0;
     }
     __syncthreads();
-    const int nl = s.wcnt_nl[K1_WARPS];
-    const int tabs_tile = s.wcnt_tab[K1_WARPS];
+    const int n_lines = mask_prefix(s.ls, s.vpre, s.scan_ws); // vpre: line-start prefix for now
+    __syncthreads();
 
     TextReader rd;
-    rd.text = a.text; rd.nbytes = a.nbytes; rd.stage_lo = t0; rd.stage_len = K1_STAGE;
-    rd.swords = reinterpret_cast<const unsigned*>(s.text); rd.word = 0;
+    rd.text = a.text; rd.nbytes = a.nbytes; rd.stage_lo = 0; rd.stage_len = 0; rd.swords = nullptr; rd.word = 0;
 
-    // the last line may run past the tile: count its tabs up to the 9th by reading on
-    if (tid == 0 && nl > 0) {
-        int tabs = tabs_tile - s.lt[nl - 1];
-        // closed inside the tile (a newline at or after its start)? then all its tabs are already counted:
-        // only blank lines can follow the last recorded line start
-        bool closed = s.last_nl >= (int)s.ls[nl - 1];
-        if (!closed && tabs < 9) {
-            rd.seek(t0 + K1_TILE);
+    // ---- phase A: one thread per line: a record iff >= 9 tabs before its newline (paf.hpp:84)
+    for (int j = tid; j < n_lines; j += K1_THREADS) {
+        int p = select_bit(s.ls, s.vpre, j);
+        int e = next_bit(s.nl, p);                 // the line's newline, or K1_STAGE when it is not staged
+        int tabs = count_bits(s.tab, p, e);
+        if (tabs < 9 && e == K1_STAGE && t0 + K1_STAGE < a.nbytes) { // runs past the staged bytes: read on
+            rd.seek(t0 + K1_STAGE);
             for (;;) { int c = rd.next(); if (c < 0 || c == '\n') break; if (c == '\t' && ++tabs >= 9) break; }
         }
-        s.last_line_tabs = tabs;
+        if (tabs >= 9) atomicOr(&s.valid[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    const int n_valid = mask_prefix(s.valid, s.vpre, s.scan_ws); // vpre: record prefix from here on
+    if (tid == 0) {
+        lookback_publish(a.status, tile, (uint64_t)n_valid);     // successors can look back while this tile decodes
     }
     __syncthreads();
 
-    // ---- phase A: validity per line -> ranks (stored over lt) and the tile's record count
-    int base = 0;
-    for (int i0 = 0; i0 < nl; i0 += K1_THREADS) {
-        int i = i0 + tid;
-        int valid = 0;
-        if (i < nl) {
-            int tabs = (i == nl - 1) ? s.last_line_tabs : (int)s.lt[i + 1] - (int)s.lt[i];
-            valid = tabs >= 9;
-        }
-        int tot;
-        int ex = block_exclusive_sum<int, K1_THREADS>(valid, s.scan_ws, &tot);
-        if (i < nl) s.lt[i] = valid ? (uint16_t)(base + ex) : (uint16_t)0xFFFF;
-        base += tot;
-        __syncthreads();
-    }
-    const int      n_valid = base;
-    const uint64_t prefix = lookback_block(a.status, tile, (uint64_t)n_valid, &s.bcast);
-    if (tid == 0 && tile == a.n_tiles - 1) *a.n_records_out = a.rec_base + (int64_t)prefix + n_valid;
-
-    // ---- phase B: decode valid lines, one per thread
+    // ---- phase B: decode.  Two threads per record when the tile's records fit (even lane: query side, odd lane: target side)
     int r0[7];
 #pragma unroll
     for (int k = 0; k < 7; k++) r0[k] = a.rec0[k];
-    for (int i = tid; i < nl; i += K1_THREADS) {
-        unsigned rank = s.lt[i];
-        if (rank == 0xFFFFu) continue;
-        int64_t rec = a.rec_base + (int64_t)prefix + rank;
-        rd.seek(t0 + s.ls[i]);
-        ParsedRec pr;
-        parse_record(rd, a.names, pr);
-        if (pr.qid < 0 || pr.tid < 0) { report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec); continue; }
-        if (rec < a.rec_cap) {
-            a.qid[rec] = pr.qid; a.tid[rec] = pr.tid; a.qs[rec] = pr.qs; a.qe[rec] = pr.qe;
-            a.ts[rec] = pr.ts; a.te[rec] = pr.te; a.strand[rec] = (uint8_t)pr.strand;
+    const unsigned* sw = reinterpret_cast<const unsigned*>(s.text);
+    const bool      pair = n_valid * 2 <= K1_THREADS;
+    const int       per_round = pair ? K1_THREADS / 2 : K1_THREADS;
+    uint64_t        prefix = 0;
+    bool            have_prefix = false;
+    for (int base = 0; base < n_valid || !have_prefix; base += per_round) {
+        const int  j = base + (pair ? (tid >> 1) : tid);
+        const bool active = j < n_valid;
+        const bool doA = active && (!pair || !(tid & 1)), doB = active && (!pair || (tid & 1));
+        int  p = 0, t4 = 0, qid = 0, tidv = 0, qs = 0, qe = 0, ts = 0, te = 0;
+        unsigned strand = 0;
+        bool staged = true;
+        if (active) p = select_bit(s.valid, s.vpre, j);
+        if (doA) {
+            int t0_ = next_bit(s.tab, p), t1 = next_bit(s.tab, t0_ + 1), t2 = next_bit(s.tab, t1 + 1), t3 = next_bit(s.tab, t2 + 1);
+            t4 = next_bit(s.tab, t3 + 1);
+            if (t4 < K1_STAGE) {
+                qid = nametable_find(a.names, hash_name_smem(sw, p, t0_, a.names.seed));
+                qs = parse_num_smem(s.text, t1 + 1, t2); qe = parse_num_smem(s.text, t2 + 1, t3);
+                strand = (t4 > t3 + 1) && s.text[t3 + 1] == '-';
+            } else staged = false;
         }
-        // chop.hpp:171-184: record k >= 1 mirrors record 0
-        if (r0[6] && (rec != 0 || !a.first_is_local) && r0[0] == pr.tid && r0[1] == pr.qid && r0[2] == pr.ts &&
-            r0[3] == pr.te && r0[4] == pr.qs && r0[5] == pr.qe)
-            *a.sym_flag = 1;
+        if (pair) t4 = __shfl_sync(FULL, t4, lane & ~1);
+        if (doB) {
+            if (t4 < K1_STAGE) {
+                int t5 = next_bit(s.tab, t4 + 1), t6 = next_bit(s.tab, t5 + 1), t7 = next_bit(s.tab, t6 + 1), t8 = next_bit(s.tab, t7 + 1);
+                if (t8 < K1_STAGE) {
+                    tidv = nametable_find(a.names, hash_name_smem(sw, t4 + 1, t5, a.names.seed));
+                    ts = parse_num_smem(s.text, t6 + 1, t7); te = parse_num_smem(s.text, t7 + 1, t8);
+                } else staged = false;
+            } else staged = false;
+        }
+        if (pair) staged = __shfl_sync(FULL, (int)staged, lane & ~1) && __shfl_sync(FULL, (int)staged, lane | 1);
+        if (active && !staged) { // the record runs past the staged bytes: byte-wise reader over global memory (both lanes of a pair)
+            ParsedRec pr;
+            rd.seek(t0 + p);
+            parse_record(rd, a.names, pr);
+            qid = pr.qid; tidv = pr.tid; qs = pr.qs; qe = pr.qe; ts = pr.ts; te = pr.te; strand = pr.strand;
+        }
+        if (!have_prefix) { prefix = lookback_wait(a.status, tile, (uint64_t)n_valid, &s.bcast); have_prefix = true; }
+        const int64_t rec = a.rec_base + (int64_t)prefix + j;
+        // symmetric predicate (chop.hpp:171-184): record k >= 1 mirrors record 0; each lane checks its half
+        bool mA = r0[1] == qid && r0[4] == qs && r0[5] == qe, mB = r0[0] == tidv && r0[2] == ts && r0[3] == te;
+        if (pair) { bool oA = __shfl_sync(FULL, (int)mA, lane & ~1), oB = __shfl_sync(FULL, (int)mB, lane | 1); mA = oA; mB = oB; }
+        if (doA) {
+            if (qid < 0) report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec);
+            else if (rec < a.rec_cap) { a.qid[rec] = qid; a.qs[rec] = qs; a.qe[rec] = qe; a.strand[rec] = (uint8_t)strand; }
+            if (r0[6] && (rec != 0 || !a.first_is_local) && mA && mB) *a.sym_flag = 1;
+        }
+        if (doB) {
+            if (tidv < 0) report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec);
+            else if (rec < a.rec_cap) { a.tid[rec] = tidv; a.ts[rec] = ts; a.te[rec] = te; }
+        }
     }
+    if (tid == 0 && tile == a.n_tiles - 1) *a.n_records_out = a.rec_base + (int64_t)prefix + n_valid;
 }
 
 // First record of the text (single thread; the first line is a record in any sane PAF).

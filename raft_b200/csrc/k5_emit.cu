@@ -13,48 +13,70 @@
 // record offsets, generates header bytes on the fly and gathers sequence bytes with aligned
 // 128-bit loads + funnel shifts + aligned 128-bit stores (stream-compacted: bytes land in their
 // final file order).
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace raftk {
 
 // ================================================================ K5a coverage.txt
-constexpr int CE_THREADS = 128;
-constexpr int CE_PER = COV_TILE_SLOTS / CE_THREADS; // 8 slots per thread
+constexpr int CE_THREADS = 256;
+constexpr int CE_PER = COV_TILE_SLOTS / CE_THREADS; // 4 slots per thread
 constexpr int CE_MAX_SLOT_BYTES = 40;               // "read 2147483647 " (16) + "2147483647,-2147483648 " (23)
-constexpr int CE_SMEM = COV_TILE_SLOTS * CE_MAX_SLOT_BYTES + 32;
+constexpr int CE_CAP = 16384;                       // shared-memory text buffer; tiles with more text (tiny reads) use the direct path
+constexpr int CE_SMEM = CE_CAP + 32;
 
-__device__ __forceinline__ int64_t find_read(const int64_t* __restrict__ slot_off, int64_t m, int64_t g)
-{ // largest i in [0,m) with slot_off[i] <= g
-    int64_t lo = 0, hi = m;
-    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (slot_off[mid] <= g) lo = mid; else hi = mid; }
-    return lo;
+// text of one slot at p; returns the end.  bin < nb: "pos,cov " ; bin == nb (sentinel): "\n"; bin == 0 is preceded by "read i "
+__device__ __forceinline__ uint8_t* cov_slot_text(uint8_t* p, int64_t read_id, int64_t bin, bool sentinel, int reso, int cov)
+{
+    if (bin == 0) {
+        p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
+        uint64_t id = (uint64_t)read_id;
+        int      nd = dec_digits64(id);
+        for (int d = nd - 1; d >= 0; d--) { p[d] = (uint8_t)('0' + (unsigned)(id % 10ull)); id /= 10ull; }
+        p += nd; *p++ = ' ';
+    }
+    if (sentinel) { *p++ = '\n'; return p; }
+    p = put_i32(p, (int32_t)(bin * reso)); *p++ = ',';
+    p = put_i32(p, cov); *p++ = ' ';
+    return p;
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(CE_THREADS) k_cov_text(CovEmitArgs a)
+__global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitArgs a)
 {
     extern __shared__ __align__(16) uint8_t sbuf[];
     __shared__ int ws[34];
     const int64_t  tile = a.tile_first + blockIdx.x;
     const int64_t  g0 = tile * COV_TILE_SLOTS + (int64_t)threadIdx.x * CE_PER;
-    int            sizes[CE_PER];
     int            mine = 0;
     int64_t        ri = 0, rs = 0, re = 0; // current read, its first slot, one past its last slot
-    if (g0 < a.n_slots) { ri = find_read(a.slot_off, a.m, g0); rs = a.slot_off[ri]; re = a.slot_off[ri + 1]; }
+    int            cv[CE_PER];
+    if (g0 < a.n_slots) {
+        // the tile map bounds the search to the reads that intersect this tile
+        int64_t lo = a.tile_read[tile], hi = (int64_t)a.tile_read[tile + 1] + 1;
+        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a.slot_off[mid] <= g0) lo = mid; else hi = mid; }
+        ri = lo; rs = a.slot_off[ri]; re = a.slot_off[ri + 1];
+    }
+    if (g0 + CE_PER <= a.n_slots) { // 4 consecutive ints, 16-byte aligned
+        int4 v = *reinterpret_cast<const int4*>(a.cov + g0);
+        cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CE_PER; k++) cv[k] = (g0 + k < a.n_slots) ? a.cov[g0 + k] : 0;
+    }
     {
         int64_t r_ = ri, rs_ = rs, re_ = re;
 #pragma unroll
         for (int k = 0; k < CE_PER; k++) {
             int64_t g = g0 + k;
-            int     sz = 0;
             if (g < a.n_slots) {
                 while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
                 int64_t bin = g - rs_;
-                if (bin == 0) sz += 5 + dec_digits64((uint64_t)(a.own_first + r_)) + 1;
-                if (g == re_ - 1) sz += 1;
-                else sz += dec_digits((uint32_t)(bin * a.reso)) + 1 + dec_len_i32(a.cov[g]) + 1;
+                if (bin == 0) mine += 5 + dec_digits64((uint64_t)(a.own_first + r_)) + 1;
+                if (g == re_ - 1) mine += 1;
+                else mine += dec_digits((uint32_t)(bin * a.reso)) + 1 + dec_len_i32(cv[k]) + 1;
             }
-            sizes[k] = sz; mine += sz;
         }
     }
     int tot;
@@ -66,6 +88,22 @@ __global__ void __launch_bounds__(CE_THREADS) k_cov_text(CovEmitArgs a)
     const int64_t o0 = a.tile_off[tile], o1 = o0 + tot;
     const int64_t c0 = o0 > a.w0 ? o0 : a.w0, c1 = o1 < a.w1 ? o1 : a.w1;
     if (c0 >= c1) return;
+    if (tot > a.text_cap) {
+        // direct path (rare: thousands of tiny reads in one tile): format privately, store byte-wise with clipping
+        uint8_t  loc[CE_PER * CE_MAX_SLOT_BYTES];
+        uint8_t* p = loc;
+        int64_t  r_ = ri, rs_ = rs, re_ = re;
+        for (int k = 0; k < CE_PER; k++) {
+            int64_t g = g0 + k;
+            if (g < a.n_slots) {
+                while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
+                p = cov_slot_text(p, a.own_first + r_, g - rs_, g == re_ - 1, a.reso, cv[k]);
+            }
+        }
+        int64_t x = o0 + ex;
+        for (uint8_t* q = loc; q < p; q++, x++) if (x >= a.w0 && x < a.w1) a.dst[x - a.w0] = *q;
+        return;
+    }
     const uintptr_t gdst0 = (uintptr_t)a.dst + (uintptr_t)(o0 - a.w0); // address of stream byte o0 (may precede dst)
     const int       phase = (int)(gdst0 & 15);
     {
@@ -76,20 +114,7 @@ __global__ void __launch_bounds__(CE_THREADS) k_cov_text(CovEmitArgs a)
             int64_t g = g0 + k;
             if (g < a.n_slots) {
                 while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
-                int64_t bin = g - rs_;
-                if (bin == 0) {
-                    p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
-                    uint64_t id = (uint64_t)(a.own_first + r_);
-                    int      nd = dec_digits64(id);
-                    for (int d = nd - 1; d >= 0; d--) { p[d] = (uint8_t)('0' + (unsigned)(id % 10ull)); id /= 10ull; }
-                    p += nd; *p++ = ' ';
-                }
-                if (g == re_ - 1) {
-                    *p++ = '\n';
-                } else {
-                    p = put_i32(p, (int32_t)(bin * a.reso)); *p++ = ',';
-                    p = put_i32(p, a.cov[g]); *p++ = ' ';
-                }
+                p = cov_slot_text(p, a.own_first + r_, g - rs_, g == re_ - 1, a.reso, cv[k]);
             }
         }
     }
@@ -105,15 +130,33 @@ __global__ void __launch_bounds__(CE_THREADS) k_cov_text(CovEmitArgs a)
     for (uintptr_t x = la + threadIdx.x; x < ga1; x += CE_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
 }
 
+// one thread per read: every tile whose first slot lies in this read's slot range points at it
+__global__ void __launch_bounds__(256) k_cov_tile_index(const int64_t* __restrict__ slot_off, int64_t m, int64_t n_tiles, int32_t* tile_read)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int64_t s0 = slot_off[i], s1 = slot_off[i + 1];
+    for (int64_t T = (s0 + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS; T * COV_TILE_SLOTS < s1 && T < n_tiles; T++) tile_read[T] = (int32_t)i;
+    if (i == m - 1) tile_read[n_tiles] = (int32_t)(m - 1);
+}
+void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, int32_t* tile_read, cudaStream_t st)
+{
+    int64_t T = (n_slots + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS;
+    if (m > 0) k_cov_tile_index<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(slot_off, m, T, tile_read);
+}
+
 int  cov_tiles(int64_t n_slots) { return (int)((n_slots + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS); }
 void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st)
 {
     int t = cov_tiles(a.n_slots);
     if (t > 0) k_cov_text<false><<<t, CE_THREADS, 0, st>>>(a);
 }
-void launch_cov_emit(const CovEmitArgs& a, int64_t n_tiles_launch, cudaStream_t st)
+void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream_t st)
 {
     if (n_tiles_launch <= 0) return;
+    CovEmitArgs a = a_in;
+    a.text_cap = CE_CAP;
+    if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CE_CAP) a.text_cap = v; } // test knob: force the direct path
     cudaFuncSetAttribute(k_cov_text<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
     k_cov_text<true><<<(unsigned)n_tiles_launch, CE_THREADS, CE_SMEM, st>>>(a);
 }
@@ -158,13 +201,40 @@ void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st)
 }
 
 // ================================================================ K5b reads.fasta
+// Output-tile-parallel gather.  CTA b owns stream bytes [T*16Ki, (T+1)*16Ki) of reads.fasta.  One thread
+// walks the records that intersect the tile (tile_frag[T] gives the first) and issues one 1-D TMA bulk
+// copy per sequence piece from the read arena into shared memory (16-byte aligned superset of the
+// piece); all threads then realign from shared memory (two aligned 128-bit shared loads + funnel
+// shifts) and store aligned 128-bit words to the output, and generate the few header bytes directly.
 constexpr int FE_THREADS = 256;
+constexpr int FE_MAXP = 24;                         // pieces staged per round
+constexpr int FE_STAGE = FASTA_TILE + FE_MAXP * 32; // staged source bytes per round
 
-// 16 bytes starting at arbitrary address p (all inside the source arena)
-__device__ __forceinline__ uint4 load_unaligned16(const uint8_t* p)
+struct FePiece {
+    long long frag;   // record index
+    long long O;      // stream offset of the record
+    long long p0;     // stream position of the first sequence byte of the piece
+    const uint8_t* src; // global address of that byte
+    int       n;      // sequence bytes of the piece inside the tile (0: header / newline only)
+    int       n_stage; // leading bytes available in shared memory (the rest is read from global)
+    int       soff;   // offset of the first byte in the stage buffer
+    int       bulk;   // bytes moved by the piece's TMA copy
+    int       h, len, read, fa;
+};
+
+struct __align__(16) FeSmem {
+    uint8_t  stage[FE_STAGE];
+    FePiece  piece[FE_MAXP];
+    uint64_t bar;
+    int      np;
+    int      more;      // records of the tile left for another round
+    long long next_g;
+};
+
+__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t* sp)
 {
-    const unsigned sa = (unsigned)((uintptr_t)p & 15);
-    const uint4*   b = reinterpret_cast<const uint4*>(p - sa);
+    const unsigned sa = (unsigned)(smem_u32(sp) & 15u);
+    const uint4*   b = reinterpret_cast<const uint4*>(sp - sa);
     uint4          q0 = b[0];
     if (sa == 0) return q0;
     uint4          q1 = b[1];
@@ -191,77 +261,170 @@ __device__ __forceinline__ uint4 load_unaligned16(const uint8_t* p)
     return o;
 }
 
-// all threads of the block copy n bytes; dst and src arbitrarily aligned
-__device__ __forceinline__ void block_copy(uint8_t* dst, const uint8_t* src, int64_t n)
+// all threads: n bytes from shared memory (any alignment) to global (any alignment)
+__device__ __forceinline__ void block_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n)
 {
-    int64_t head = (int64_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
-    for (int64_t k = threadIdx.x; k < head; k += FE_THREADS) dst[k] = src[k];
-    const int64_t nbody = (n - head) >> 4;
-    uint4*        d16 = reinterpret_cast<uint4*>(dst + head);
-    const uint8_t* s = src + head;
-    for (int64_t c = threadIdx.x; c < nbody; c += FE_THREADS) stg_stream(d16 + c, load_unaligned16(s + (c << 4)));
-    const int64_t done = head + (nbody << 4);
-    for (int64_t k = done + threadIdx.x; k < n; k += FE_THREADS) dst[k] = src[k];
+    for (int k = threadIdx.x; k < head; k += FE_THREADS) dst[k] = sp[k];
+    const int nbody = (n - head) >> 4;
+    uint4*    d16 = reinterpret_cast<uint4*>(dst + head);
+    const uint8_t* s = sp + head;
+    for (int c = threadIdx.x; c < nbody; c += FE_THREADS) stg_stream(d16 + c, lds_unaligned16(s + (c << 4)));
+    const int done = head + (nbody << 4);
+    for (int k = done + threadIdx.x; k < n; k += FE_THREADS) dst[k] = sp[k];
 }
 
-__global__ void __launch_bounds__(FE_THREADS) k_fasta_emit(FastaEmitArgs a)
+__global__ void __launch_bounds__(256) k_fasta_tile_index(const int64_t* __restrict__ frag_off, int64_t G, int64_t n_tiles, int32_t* tile_frag)
 {
-    const int64_t lead = (int64_t)((uintptr_t)a.dst & 15);
-    const int64_t xs = a.w0 - lead + (int64_t)blockIdx.x * FASTA_TILE;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    int64_t o0 = frag_off[g], o1 = frag_off[g + 1];
+    for (int64_t T = (o0 + FASTA_TILE - 1) / FASTA_TILE; T * FASTA_TILE < o1 && T < n_tiles; T++) tile_frag[T] = (int32_t)g;
+}
+void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st)
+{
+    // the caller sizes tile_frag for ceil(total/FASTA_TILE) tiles; every tile start lies inside exactly one record
+    if (G > 0) k_fasta_tile_index<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(frag_off, G, (int64_t)1 << 62, tile_frag);
+}
+
+__global__ void __launch_bounds__(256) k_frag_desc(const int32_t* __restrict__ frag_read, const int32_t* __restrict__ frag_a,
+                                                   const int32_t* __restrict__ frag_b, const int32_t* __restrict__ frag_size,
+                                                   const int64_t* __restrict__ frag_off, const int64_t* __restrict__ seq_off, int64_t G, FragDesc* desc)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G) return;
+    FragDesc d{};
+    d.out_off = frag_off[g];
+    if (g < G) {
+        int i = frag_read[g], fa = frag_a[g], fb = frag_b[g];
+        d.src_off = seq_off[i] + fa; d.len = fb - fa; d.hdr_len = frag_size[g] - (fb - fa) - 1; d.read = i; d.a = fa;
+    }
+    desc[g] = d;
+}
+void launch_frag_desc(const int32_t* frag_read, const int32_t* frag_a, const int32_t* frag_b, const int32_t* frag_size, const int64_t* frag_off,
+                      const int64_t* seq_off, int64_t G, FragDesc* desc, cudaStream_t st)
+{
+    k_frag_desc<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(frag_read, frag_a, frag_b, frag_size, frag_off, seq_off, G, desc);
+}
+
+__global__ void __launch_bounds__(FE_THREADS, 5) k_fasta_emit(FastaEmitArgs a)
+{
+    extern __shared__ __align__(16) uint8_t fe_raw[];
+    FeSmem& s = *reinterpret_cast<FeSmem*>(fe_raw);
+    const int64_t T = a.w0 / FASTA_TILE + blockIdx.x;
+    const int64_t xs = T * FASTA_TILE;
     const int64_t x0 = xs > a.w0 ? xs : a.w0;
     const int64_t x1 = (xs + FASTA_TILE) < a.w1 ? (xs + FASTA_TILE) : a.w1;
     if (x0 >= x1) return;
-    // first record intersecting the tile: largest g with frag_off[g] <= x0
-    int64_t lo = 0, hi = a.G;
-    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a.frag_off[mid] <= x0) lo = mid; else hi = mid; }
-    for (int64_t g = lo; g < a.G; g++) {
-        const int64_t O = a.frag_off[g];
-        if (O >= x1) break;
-        const int64_t  O1 = a.frag_off[g + 1];
-        const int64_t  i = a.frag_read[g];
-        const int      fa = a.frag_a[g], fb = a.frag_b[g];
-        const int64_t  gid = a.own_first + i;
-        const int64_t  nm0 = a.name_off[gid];
-        const int      nl = (int)(a.name_off[gid + 1] - nm0);
-        const uint64_t num = (uint64_t)(a.read_num_base + g + 1);
-        const int      dn = dec_digits64(num), da = dec_digits((uint32_t)fa), db = dec_digits((uint32_t)fb);
-        const int      h = 6 + dn + 1 + nl + 22 + da + 1 + db + 1;
-        const int64_t  len = (int64_t)fb - fa;
-        // header bytes [O, O+h)
-        {
-            int64_t p0 = O > x0 ? O : x0, p1 = (O + h) < x1 ? (O + h) : x1;
-            for (int64_t x = p0 + threadIdx.x; x < p1; x += FE_THREADS) {
-                int     k = (int)(x - O);
-                uint8_t c;
-                if (k < 6) c = (uint8_t)(">read="[k]);
-                else if ((k -= 6) < dn) c = dec_digit_at(num, dn, k);
-                else if ((k -= dn) < 1) c = ',';
-                else if ((k -= 1) < nl) c = a.names[nm0 + k];
-                else if ((k -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[k]);
-                else if ((k -= 22) < da) c = dec_digit_at((uint64_t)fa, da, k);
-                else if ((k -= da) < 1) c = '-';
-                else if ((k -= 1) < db) c = dec_digit_at((uint64_t)fb, db, k);
-                else c = '\n';
-                a.dst[x - a.w0] = c;
+    if (threadIdx.x == 0) {
+        mbar_init(&s.bar, 1);
+        s.next_g = a.tile_frag[T]; // record containing the tile's first byte
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    for (;;) {
+        // ---- one thread: list the pieces of this round and start their TMA copies
+        if (threadIdx.x == 0) {
+            int     np = 0, used = 0;
+            int64_t g = s.next_g;
+            bool    more = false;
+            for (; g < a.G; g++) {
+                const FragDesc d = a.desc[g];
+                const int64_t  O = d.out_off;
+                if (O >= x1) break;
+                const int64_t s0 = O + d.hdr_len, s1 = s0 + d.len;
+                if (s1 + 1 <= x0) continue;                               // the window starts after this record
+                if (np == FE_MAXP) { more = true; break; }
+                const int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
+                FePiece&      pc = s.piece[np];
+                pc.frag = g; pc.O = O; pc.p0 = p0; pc.n = p1 > p0 ? (int)(p1 - p0) : 0; pc.n_stage = 0; pc.soff = 0; pc.bulk = 0; pc.src = nullptr;
+                pc.h = d.hdr_len; pc.len = d.len; pc.read = d.read; pc.fa = d.a;
+                if (pc.n > 0) {
+                    const int64_t srcoff = d.src_off + (p0 - s0);         // offset in the arena
+                    const int64_t al = srcoff & ~(int64_t)15;
+                    int64_t       end = (srcoff + pc.n + 15) & ~(int64_t)15;
+                    if (end > a.seq_safe_end) end = a.seq_safe_end;       // never read past what the arena guarantees
+                    const int bytes = end > al ? (int)(end - al) : 0;
+                    if (used + bytes > FE_STAGE) { more = true; break; }  // next round
+                    pc.src = a.seq + srcoff;
+                    pc.soff = used + (int)(srcoff - al);
+                    const int avail = bytes - (int)(srcoff - al);
+                    pc.n_stage = avail < 0 ? 0 : (avail > pc.n ? pc.n : avail);
+                    pc.bulk = bytes;
+                    used += bytes;
+                }
+                np++;
+            }
+            s.np = np; s.next_g = g; s.more = more ? 1 : 0;
+            if (used > 0) {
+                mbar_expect_tx(&s.bar, (uint32_t)used);
+                int off = 0;
+                for (int k = 0; k < np; k++) {
+                    const FePiece& pc = s.piece[k];
+                    if (pc.bulk > 0) {
+                        tma_load_1d(s.stage + off, pc.src - (pc.soff - off), (uint32_t)pc.bulk, &s.bar);
+                        off += pc.bulk;
+                    }
+                }
+            } else {
+                // nothing staged this round: complete the phase by hand so that the wait below falls through
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bar)) : "memory");
             }
         }
-        // sequence bytes [O+h, O+h+len)
-        {
-            int64_t s0 = O + h, s1 = s0 + len;
-            int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
-            if (p0 < p1) block_copy(a.dst + (p0 - a.w0), a.seq + a.seq_off[i] + fa + (p0 - s0), p1 - p0);
+        __syncthreads();
+        // ---- all threads: header bytes and newlines first (no dependence on the copies), then the staged sequence bytes
+        const int np = s.np;
+        for (int k = 0; k < np; k++) {
+            const FePiece& pc = s.piece[k];
+            const int64_t  O = pc.O;
+            const int      h = pc.h;
+            const int64_t  hp0 = O > x0 ? O : x0, hp1 = (O + h) < x1 ? (O + h) : x1;
+            if (hp0 < hp1) {
+                const int64_t  gid = a.own_first + pc.read;
+                const uint64_t num = (uint64_t)(a.read_num_base + pc.frag + 1);
+                const int      fa = pc.fa, fb = pc.fa + pc.len;
+                const int64_t  nm0 = a.name_off[gid];
+                const int      nl = (int)(a.name_off[gid + 1] - nm0);
+                const int      dn = dec_digits64(num), da = dec_digits((uint32_t)fa), db = dec_digits((uint32_t)fb);
+                for (int64_t x = hp0 + threadIdx.x; x < hp1; x += FE_THREADS) {
+                    int     q = (int)(x - O);
+                    uint8_t c;
+                    if (q < 6) c = (uint8_t)(">read="[q]);
+                    else if ((q -= 6) < dn) c = dec_digit_at(num, dn, q);
+                    else if ((q -= dn) < 1) c = ',';
+                    else if ((q -= 1) < nl) c = a.names[nm0 + q];
+                    else if ((q -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[q]);
+                    else if ((q -= 22) < da) c = dec_digit_at((uint64_t)fa, da, q);
+                    else if ((q -= da) < 1) c = '-';
+                    else if ((q -= 1) < db) c = dec_digit_at((uint64_t)fb, db, q);
+                    else c = '\n';
+                    a.dst[x - a.w0] = c;
+                }
+            }
+            const int64_t s1 = O + h + pc.len;
             if (threadIdx.x == 0 && s1 >= x0 && s1 < x1) a.dst[s1 - a.w0] = '\n';
         }
-        (void)O1;
+        mbar_wait(&s.bar, phase);
+        phase ^= 1;
+        for (int k = 0; k < np; k++) {
+            const FePiece& pc = s.piece[k];
+            if (pc.n > 0) {
+                uint8_t* d = a.dst + (pc.p0 - a.w0);
+                block_copy_from_smem(d, s.stage + pc.soff, pc.n_stage);
+                for (int q = pc.n_stage + threadIdx.x; q < pc.n; q += FE_THREADS) d[q] = pc.src[q]; // arena tail not covered by the bulk copy
+            }
+        }
+        if (!s.more) break;
+        __syncthreads(); // the stage and the piece list are rewritten by the next round
     }
 }
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
 {
     if (a.w1 <= a.w0 || a.G <= 0) return;
-    int64_t lead = (int64_t)((uintptr_t)a.dst & 15);
-    int64_t tiles = (a.w1 - a.w0 + lead + FASTA_TILE - 1) / FASTA_TILE;
-    k_fasta_emit<<<(unsigned)tiles, FE_THREADS, 0, st>>>(a);
+    int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
+    cudaFuncSetAttribute(k_fasta_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
+    k_fasta_emit<<<(unsigned)tiles, FE_THREADS, sizeof(FeSmem), st>>>(a);
 }
 
 // ================================================================ digest

@@ -126,7 +126,11 @@ struct CovEmitArgs {
     uint8_t*       dst;       // window buffer: byte (w0 + k) of the stream goes to dst[k]
     int64_t        w0, w1;
     int64_t        tile_first; // first tile of this launch
+    const int32_t* tile_read;  // n_tiles+1: read containing the tile's first slot (last entry = m-1 sentinel)
+    int            text_cap;   // tiles with more text than this take the direct (byte-wise) path
 };
+// tile_read[T] = read whose slots contain slot T*COV_TILE_SLOTS
+void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, int32_t* tile_read, cudaStream_t st);
 int  cov_tiles(int64_t n_slots);
 void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st);
 void launch_cov_emit(const CovEmitArgs& a, int64_t n_tiles_launch, cudaStream_t st);
@@ -144,9 +148,19 @@ struct RepEmitArgs {
 void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st);
 
 constexpr int FASTA_TILE = 16384;
+// everything the gather needs about one FASTA record, one 32-byte load
+struct __align__(32) FragDesc {
+    long long out_off; // stream offset of the record's '>'
+    long long src_off; // arena offset of its first base (seq_off[read] + a)
+    int       len;     // bases (b - a)
+    int       hdr_len; // header bytes including its newline
+    int       read;    // local read index
+    int       a;       // first base on the original read
+};
+void launch_frag_desc(const int32_t* frag_read, const int32_t* frag_a, const int32_t* frag_b, const int32_t* frag_size, const int64_t* frag_off,
+                      const int64_t* seq_off, int64_t G, FragDesc* desc, cudaStream_t st);
 struct FastaEmitArgs {
-    const int32_t *frag_read, *frag_a, *frag_b;
-    const int64_t* frag_off; // G+1 byte offsets of the records
+    const FragDesc* desc;    // G+1 (last: out_off = stream length)
     int64_t        G;
     const uint8_t* seq;      // local arena
     const int64_t* seq_off;  // local m+1
@@ -154,8 +168,11 @@ struct FastaEmitArgs {
     const int64_t* name_off; // global
     int64_t        own_first, read_num_base;
     uint8_t*       dst;
-    int64_t        w0, w1;   // stream window; tile t covers [w0a + t*TILE, ...) with w0a = w0 rounded down to the tile grid of dst
+    int64_t        w0, w1;   // stream window; CTA b covers stream bytes [(w0/TILE + b)*TILE, +TILE) clipped to it
+    const int32_t* tile_frag; // record containing stream byte T*FASTA_TILE, for every tile of the stream
+    int64_t        seq_safe_end; // bytes of the arena that may be read in 16-byte blocks (multiple of 16)
 };
+void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st);
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st);
 
 void launch_digest(const uint8_t* buf, int64_t n, int64_t abs_off, unsigned long long* acc, cudaStream_t st);

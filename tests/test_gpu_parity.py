@@ -172,3 +172,95 @@ def test_cli_binary_against_golden():
                 check_output(entry, suf, open(os.path.join(d, "out." + suf), "rb").read())
             got = [l for l in r.stdout.decode().splitlines() if not l.startswith("INFO, main(), program completed") and "CMD:" not in l]
             assert got == entry["stdout"], entry["name"]
+
+
+def _stress_paf(ds, seed=0):
+    """PAF text with everything the tokenizer's mask logic can trip on: lines longer than the staged
+    overhang (kilobyte tags), lines crossing 16 KiB tile boundaries, blank-line runs, short lines,
+    exactly-10-field lines, CRLF, numeric fields with spaces / signs / junk."""
+    rng = np.random.default_rng(seed)
+    lines = ds.paf.split(b"\n")[:-1]
+    out = []
+    for k, ln in enumerate(lines[:6000]):
+        r = rng.integers(0, 20)
+        f = ln.split(b"\t")
+        if r == 0:
+            out.append(b"")                                   # blank line
+            out.append(ln)
+        elif r == 1:
+            out.append(b"\t".join(f[:9]))                    # 9 fields: not a record
+        elif r == 2:
+            out.append(b"\t".join(f[:10]))                   # 10 fields: a record
+        elif r == 3:
+            out.append(ln + b"\tcg:Z:" + b"5M1D" * int(rng.integers(100, 12000)))  # very long tag
+        elif r == 4:
+            out.append(ln + b"\r")                           # CRLF
+        elif r == 5:
+            f2 = list(f); f2[2] = b" " + f2[2]; f2[3] = b"+" + f2[3]; f2[8] = f2[8] + b"xyz"; f2[7] = b"0" + f2[7]
+            out.append(b"\t".join(f2))
+        elif r == 6:
+            out.append(b"\n\n\n" + ln)                       # run of blank lines
+        elif r == 7:
+            out.append(b"garbage without tabs " * int(rng.integers(1, 200)))
+        elif r == 8:
+            out.append(b"x" * int(rng.integers(1000, 40000)) + b"\t" + ln)  # first field (name) longer than the overhang: unknown name? no: keep short-field line invalid
+            out[-1] = out[-1].replace(b"\t", b" ")         # ... make it a tab-free garbage line
+        else:
+            out.append(ln)
+    return b"\n".join(out) + (b"\n" if seed % 2 == 0 else b"")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_tokenizer_stress(seed):
+    ds = synth.make_dataset("C1", 0.05, seed % 2 == 0, seed=40 + seed)
+    paf = _stress_paf(ds, seed)
+    p = api.AlgoParams.from_args(ds.args)
+    ref = O.run(ds.reads, paf, O.make_params(**args_to_kw(ds.args)))
+    assert ref.status == 0 and ref.n_rec > 1000
+    ctx, st = gpu_run(ds.reads, paf, p)
+    compare_all(ctx, st, ref)
+    ctx.close()
+    # and the same text in awkward chunks
+    cuts = sorted(set(int(x) for x in np.random.default_rng(seed).integers(0, len(paf), 7)))
+    chunks = [b - a for a, b in zip([0] + cuts, cuts + [len(paf)])]
+    ctx, st = gpu_run(ds.reads, paf, p, chunks=chunks)
+    compare_all(ctx, st, ref)
+    ctx.close()
+
+
+def test_coverage_emitter_direct_path(monkeypatch):
+    """Tiles whose text exceeds the shared-memory buffer are written byte-wise: force that path."""
+    ds = synth.make_dataset("C5", 0.002, True, seed=12)
+    p = api.AlgoParams.from_args(ds.args)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    monkeypatch.setenv("RAFT_B200_COV_CAP", "1000")
+    ctx, st = gpu_run(ds.reads, ds.paf, p)
+    assert ctx.fetch(api.OUT_COVERAGE) == ref.cov_txt
+    total = len(ref.cov_txt)
+    for off, ln in ((7, 333), (total // 2, 70001), (total - 9, 9)):
+        assert ctx.fetch(api.OUT_COVERAGE, off, ln) == ref.cov_txt[off:off + ln]
+    ctx.close()
+
+
+def test_many_tiny_reads_and_fragments():
+    """Thousands of records per 16 KiB output tile (multi-round gather) and zero-length reads."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    lens = rng.integers(0, 40, n)
+    lens[::7] = 0
+    names = [b"t%d" % i for i in range(n)]
+    fa = b"".join(b">" + nm + b"\n" + bytes(rng.choice(list(b"ACGT"), int(L)).astype(np.uint8)) + b"\n" for nm, L in zip(names, lens))
+    reads = O.parse_fasta(fa)
+    assert reads.n == n
+    lines = []
+    for i in range(0, n - 1, 3):
+        if lens[i] > 4 and lens[i + 1] > 4:
+            lines.append(b"\t".join([names[i], b"%d" % lens[i], b"1", b"%d" % lens[i], b"+", names[i + 1], b"%d" % lens[i + 1], b"0",
+                                     b"%d" % (lens[i + 1] - 1), b"3", b"3", b"60"]))
+    paf = b"\n".join(lines) + b"\n"
+    kw = dict(est_cov=1, reso=5, repeat_length=10, read_length=20, overlap_length=3, flanking_length=2)
+    ref = O.run(reads, paf, O.make_params(**kw))
+    assert ref.status == 0
+    ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
+    compare_all(ctx, st, ref)
+    ctx.close()
