@@ -1,0 +1,230 @@
+"""Multi-GPU fragmentation: one process per GPU, reads partitioned into contiguous id ranges.
+
+The reference has no distributed mode; the path shards naturally because the
+coverage of a read depends only on the records that name it (repeat.hpp:48-58) and everything after
+coverage is per read.  Protocol per rank (`run_rank`):
+
+  1. every rank tokenises its byte range of the PAF (split at newlines) against the full name table;
+  2. record 0 of the whole file (chop.hpp:171-184 compares every later record with it) is taken from
+     the first rank that has a record and broadcast; the symmetric flag is the max over ranks;
+  3. every contributing interval becomes a 12-byte endpoint (global read id, start, end) for the
+     rank that owns the read: counts all-to-all, then ONE data all-to-all (NCCL over NVLink);
+  4. each rank accumulates the endpoints it received, finalises its own reads, and the global
+     `read=` numbering is fixed by an all-gather of fragment counts (chop.hpp:195,266,319).
+
+Each rank's outputs are a contiguous slice of each output file, in read order.
+`engine` is anything with the raft_b200.api.Context methods used below (the CPU tests plug in a
+numpy stand-in); `comm` wraps torch.distributed.
+"""
+import numpy as np
+
+
+def partition_reads(lengths, reso, world):
+    """Read-id range boundaries (int64[world+1]) balanced by coverage slots (bins + 1 per read)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    slots = (lengths + reso - 1) // reso + 1
+    csum = np.concatenate([[0], np.cumsum(slots)])
+    total = csum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(csum, total * r // world, side="left")))
+    bounds.append(len(lengths))
+    return np.maximum.accumulate(np.asarray(bounds, dtype=np.int64))
+
+
+def split_text(nbytes, world, find_newline):
+    """Byte ranges of a PAF for `world` ranks: rank r starts right after the first newline at or after
+    nbytes*r/world (rank 0 at 0).  `find_newline(pos)` returns the offset of the first '\\n' at or after pos,
+    or -1."""
+    starts = [0]
+    for r in range(1, world):
+        p = nbytes * r // world
+        nl = find_newline(p) if p > 0 else -1
+        starts.append(nbytes if nl < 0 else nl + 1)
+    starts.append(nbytes)
+    starts = np.maximum.accumulate(np.asarray(starts, dtype=np.int64))
+    return [(int(starts[r]), int(starts[r + 1])) for r in range(world)]
+
+
+class TorchComm:
+    """torch.distributed plumbing (nccl on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, dist, device, buf_device=None):
+        """device: where collectives run (cuda for nccl, cpu for gloo); buf_device: where endpoint buffers live
+        (defaults to device; a CUDA buf_device with a cpu `device` stages the exchange through host memory)."""
+        import torch
+        self.dist, self.device, self.torch = dist, device, torch
+        self.buf_device = device if buf_device is None else buf_device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def all_gather_i64(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.int64, device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def all_to_all_counts(self, counts):
+        t = self.torch.tensor(np.asarray(counts, dtype=np.int64), device=self.device)
+        out = self.torch.empty_like(t)
+        self.dist.all_to_all_single(out, t)
+        return out.cpu().numpy()
+
+    def alloc_i32(self, n):
+        return self.torch.empty(max(int(n), 1), dtype=self.torch.int32, device=self.buf_device)
+
+    def all_to_all_v(self, recv, send, recv_counts, send_counts):
+        n_s, n_r = int(sum(send_counts)), int(sum(recv_counts))
+        osz, isz = [int(c) for c in recv_counts], [int(c) for c in send_counts]
+        if self.buf_device == self.device:
+            self.dist.all_to_all_single(recv[:n_r], send[:n_s], output_split_sizes=osz, input_split_sizes=isz)
+        else:  # staged (tests: gloo collectives with CUDA buffers)
+            r = self.torch.empty(max(n_r, 1), dtype=self.torch.int32, device=self.device)
+            self.dist.all_to_all_single(r[:n_r], send[:n_s].to(self.device), output_split_sizes=osz, input_split_sizes=isz)
+            recv[:n_r].copy_(r[:n_r])
+
+
+def run_rank(engine, comm, bounds, text, nbytes):
+    """Steps 1-4 for one rank.  Returns (stats, info dict)."""
+    rank, world = comm.rank, comm.world
+    # -- record 0 of the whole file
+    rec, found = engine.peek_first_record(text, nbytes)
+    allrec = comm.all_gather_i64([1 if found else 0] + list(rec))
+    holders = [r for r in range(world) if allrec[r][0]]
+    if holders:
+        h = holders[0]
+        engine.set_first_record([int(x) for x in allrec[h][1:7]], is_local=(h == rank))
+    else:
+        engine.set_first_record(None, is_local=False)
+    # -- tokenise the local byte range
+    engine.ingest_paf(text, nbytes, last=True)
+    # -- symmetric flag: OR over ranks
+    sym = int(comm.all_gather_i64([engine.get_symmetric()]).max())
+    engine.set_symmetric(sym)
+    # -- route endpoints to the owners of their reads
+    counts = engine.route_count(bounds)
+    recv_counts = comm.all_to_all_counts(counts)
+    send = comm.alloc_i32(3 * int(counts.sum()))
+    engine.route_pack(bounds, counts, send)
+    recv = comm.alloc_i32(3 * int(recv_counts.sum()))
+    comm.all_to_all_v(recv, send, 3 * recv_counts, 3 * counts)
+    engine.accumulate_endpoints(recv, int(recv_counts.sum()))
+    # -- local coverage / repeats / cut points, then global numbering
+    st = engine.finalize()
+    per_rank = comm.all_gather_i64([int(st.n_fragments), int(st.n_records)])
+    first_num = 1 + int(per_rank[:rank, 0].sum())
+    engine.set_output_base(first_num)
+    info = dict(symmetric=sym, sent=int(counts.sum()), received=int(recv_counts.sum()), first_read_num=first_num,
+                n_records_total=int(per_rank[:, 1].sum()), n_fragments_total=int(per_rank[:, 0].sum()),
+                sent_remote=int(counts.sum() - counts[rank]))
+    return st, info
+
+
+# ------------------------------------------------------------------------------------------- bench (N > 1)
+def bench(a, rank, world, local, log):
+    """Weak-scaling bench: every rank carries `a.scale` of the config (genome scale a.scale*world in total)."""
+    import json
+    import os
+    import torch
+    import torch.distributed as dist
+    from . import api, synth_gpu
+
+    dev = torch.device("cuda", local)
+    comm = TorchComm(dist, dev)
+    WINDOW = 1 << 30
+    ds = synth_gpu.make_dataset_gpu(a.config, a.scale * world, device=f"cuda:{local}", with_seq=False, line_slice=(rank, world))
+    p = api.AlgoParams.from_args(ds.args)
+    lengths = ds.lengths.cpu().numpy()
+    bounds = partition_reads(lengths, p.reso, world)
+    b0, b1 = int(bounds[rank]), int(bounds[rank + 1])
+    own_seq = synth_gpu.gen_seq(ds, b0, b1)
+    own_off = (ds.seq_off[b0:b1 + 1] - ds.seq_off[b0]).contiguous()
+    torch.cuda.synchronize()
+    log(f"[bench r{rank}] reads {b0}..{b1} of {ds.n}, {own_seq.numel()} bases, local PAF {ds.paf.numel()} bytes / {ds.n_overlaps} lines")
+    ctx = api.Context(p, local)
+    win = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
+
+    def step(host=None):
+        if host is None:
+            ctx.set_reads_sharded(ds.n, ds.lengths, ds.name_off, ds.names, b0, b1 - b0, own_off, own_seq)
+            st, info = run_rank(ctx, comm, bounds, ds.paf, ds.paf.numel())
+            dst = win
+        else:
+            ctx.set_reads_sharded(ds.n, host["lengths"], host["name_off"], host["names"], b0, b1 - b0, host["own_off"], host["own_seq"])
+            st, info = run_rank(ctx, comm, bounds, host["paf"], ds.paf.numel())
+            dst = host["out"].data_ptr()
+        nout = 0
+        for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+            n = ctx.output_size(which)
+            for off in range(0, n, WINDOW):
+                ctx.fetch_into(which, off, dst, min(WINDOW, n - off))
+            nout += n
+        return st, info, nout
+
+    def timed(k, host=None):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            st, info, nout = step(host)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        return float(t), st, info, nout
+
+    for _ in range(a.warmup):
+        step()
+    from bench import ClockSampler
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, st, info, nout = timed(a.steps)
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.stats().kernel_launches * a.steps
+    fasta_ms = ctx.stats().ms_emit[3]
+    tot = comm.all_gather_i64([info["sent_remote"], nout, int(own_seq.numel()), int(ds.paf.numel()), launches])
+    e2e = None
+    if not a.no_e2e:
+        host = dict(lengths=ds.lengths.cpu().pin_memory().numpy(), name_off=ds.name_off.cpu().pin_memory().numpy(),
+                    names=ds.names.cpu().pin_memory().numpy(), own_off=own_off.cpu().pin_memory().numpy(),
+                    own_seq=own_seq.cpu().pin_memory().numpy(), paf=ds.paf.cpu().pin_memory().numpy(),
+                    out=torch.empty(WINDOW, dtype=torch.uint8).pin_memory())
+        step(host)
+        k = max(1, min(a.steps, 3))
+        ms_e, _, _, nout_e = timed(k, host)
+        h2d = sum(int(v.nbytes) for kk, v in host.items() if kk != "out")
+        io = comm.all_gather_i64([h2d, nout_e])
+        e2e = {"value": info["n_records_total"] / (ms_e / 1e3), "unit": "overlaps/s", "h2d_bytes_per_step": int(io[:, 0].sum()),
+               "d2h_bytes_per_step": int(io[:, 1].sum()), "ms_per_step": ms_e, "steps": k}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_alg = int(tot[:, 1].sum() + tot[:, 2].sum() + tot[:, 3].sum()) + world * int(ds.names.numel())
+        out = {"metric": "PAF overlaps/sec end-to-end fragmentation", "value": info["n_records_total"] / (ms / 1e3), "unit": "overlaps/s",
+               "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
+               "config": {"workload": f"{a.config} human 32x ONT-Duplex-shaped reads + symmetric all-vs-all PAF, genome scale {a.scale:g} per GPU "
+                                      f"({a.scale * world:g} in total), reads sharded by id range, PAF split by byte range",
+                          "n_overlaps": info["n_records_total"], "n_reads": ds.n, "bases": int(tot[:, 2].sum()),
+                          "paf_bytes": int(tot[:, 3].sum()), "out_bytes_total": int(tot[:, 1].sum()),
+                          "exchange": {"endpoints_sent_to_other_ranks": int(tot[:, 0].sum()), "bytes": 12 * int(tot[:, 0].sum()),
+                                       "collective": "all_to_all_single (NCCL) of 12-byte endpoints + counts"},
+                          "l2": "inputs and outputs are GBs per rank (>> 126 MB L2); no explicit flush"},
+               "gbp_per_s": int(tot[:, 2].sum()) / (ms / 1e3) / 1e9,
+               "roofline": {"kernel": "k_fasta_emit", "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
+                            "achieved": None if not fasta_ms else 2.0 * nout * 0.98 / (fasta_ms / 1e3) / 1e9,
+                            "frac": None if not fasta_ms else 2.0 * nout * 0.98 / (fasta_ms / 1e3) / 1e9 / peak,
+                            "note": "rank 0's gather kernel; algorithmic bytes ~ 2 x its reads.fasta bytes"},
+               "path_roofline": {"bytes_alg": bytes_alg, "achieved_gbs_per_gpu": bytes_alg / world / (ms / 1e3) / 1e9,
+                                 "frac": bytes_alg / world / (ms / 1e3) / 1e9 / peak},
+               "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(tot[:, 4].sum()), "clocks": clk}
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -61,7 +61,7 @@ def _pairs(lo, hi, min_ovl):
 
 
 def make_dataset_gpu(name, scale=1.0, symmetric=True, seed=None, device="cuda:0", min_ovl=2000, with_seq=True,
-                     read_slice=None) -> GpuDataset:
+                     read_slice=None, line_slice=None) -> GpuDataset:
     cfg = synth.CONFIGS[name]
     seed = cfg["seed"] if seed is None else seed
     dev = torch.device(device)
@@ -151,6 +151,11 @@ def make_dataset_gpu(name, scale=1.0, symmetric=True, seed=None, device="cuda:0"
         # PAF lines whose query falls in [lo, hi): the byte range of the PAF file one rank would read
         keep = (q >= read_slice[0]) & (q < read_slice[1])
         q, t, qs, qe, ts, te, rev = (x[keep] for x in (q, t, qs, qe, ts, te, rev))
+    if line_slice is not None:
+        # lines [N*r/P, N*(r+1)/P): the byte range of the PAF file that rank r of P would read
+        r_, P_ = line_slice
+        lo_l, hi_l = q.numel() * r_ // P_, q.numel() * (r_ + 1) // P_
+        q, t, qs, qe, ts, te, rev = (x[lo_l:hi_l] for x in (q, t, qs, qe, ts, te, rev))
     N = q.numel()
 
     # ---- PAF text
