@@ -155,9 +155,12 @@ int raftgpu_peek_first_record(raftgpu_ctx *ctx, const uint8_t *text, size_t nbyt
 int raftgpu_set_first_record(raftgpu_ctx *ctx, const int32_t rec[6], int32_t is_local);
 int raftgpu_get_symmetric(raftgpu_ctx *ctx, int32_t *flag);  /* local OR over this rank's records */
 int raftgpu_set_symmetric(raftgpu_ctx *ctx, int32_t flag);   /* global value after the all-reduce */
-/* Count / pack the 12-byte endpoint records (global read id, start, end) this rank must send to
- * each of nranks owners; bounds[nranks+1] are the read-id range boundaries.  counts are int64[nranks];
- * sendbuf is device memory of at least 12*sum(counts) bytes, laid out by destination rank. */
+/* Add the intervals of this rank's own records that fall on reads it owns (no exchange needed for those). */
+int raftgpu_accumulate_local(raftgpu_ctx *ctx);
+/* Count / pack the 12-byte endpoint records (global read id, start, end) this rank must send to the
+ * OTHER owners (reads owned by this rank are covered by raftgpu_accumulate_local; its own count is 0);
+ * bounds[nranks+1] are the read-id range boundaries.  counts are int64[nranks]; sendbuf is device
+ * memory of at least 12*sum(counts) bytes, laid out by destination rank. */
 int raftgpu_route_count(raftgpu_ctx *ctx, int nranks, const int64_t *bounds, int64_t *counts);
 int raftgpu_route_pack(raftgpu_ctx *ctx, int nranks, const int64_t *bounds, const int64_t *counts, void *sendbuf_device);
 /* Add routed endpoints (device memory, 12 bytes each) owned by this rank into its coverage. */

@@ -13,7 +13,7 @@ SYMBOLS = [
     "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_digest",
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
-    "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
+    "raftgpu_accumulate_local", "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
         "raftgpu_set_symmetric": (C.c_int, [vp, i32]),
         "raftgpu_route_count": (C.c_int, [vp, C.c_int, vp, vp]),
         "raftgpu_route_pack": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "raftgpu_accumulate_local": (C.c_int, [vp]),
         "raftgpu_accumulate_endpoints": (C.c_int, [vp, vp, i64]),
         "raftgpu_finalize": (C.c_int, [vp, PS]),
         "raftgpu_set_output_base": (C.c_int, [vp, i64]),

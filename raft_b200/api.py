@@ -194,6 +194,9 @@ class Context:
     def route_pack(self, bounds: np.ndarray, counts: np.ndarray, sendbuf):
         self._ck(self.L.raftgpu_route_pack(self._h, len(counts), bounds.ctypes.data, counts.ctypes.data, _ptr(sendbuf)))
 
+    def accumulate_local(self):
+        self._ck(self.L.raftgpu_accumulate_local(self._h))
+
     def accumulate_endpoints(self, ep, count):
         self._ck(self.L.raftgpu_accumulate_endpoints(self._h, _ptr(ep), count))
 

@@ -556,6 +556,20 @@ static int accumulate_local(raftgpu_ctx* ctx)
     return RAFTGPU_OK;
 }
 
+extern "C" int raftgpu_accumulate_local(raftgpu_ctx* ctx)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads || !ctx->paf_done || ctx->finalized) FAIL(RAFTGPU_E_STATE, "raftgpu_accumulate_local: wrong state");
+    CK(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev[2], ctx->st);
+    int st = accumulate_local(ctx);
+    if (st) return st;
+    cudaEventRecord(ctx->ev[3], ctx->st);
+    CK(cudaStreamSynchronize(ctx->st));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->stats.ms_scatter += ms;
+    return RAFTGPU_OK;
+}
+
 extern "C" int raftgpu_accumulate_endpoints(raftgpu_ctx* ctx, const void* ep, int64_t count)
 {
     if (!ctx || count < 0 || (count && !ep)) return RAFTGPU_E_ARG;

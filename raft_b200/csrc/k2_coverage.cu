@@ -232,11 +232,13 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
     // each block owns a contiguous chunk of records so that packing is deterministic per block
     int64_t per = (a.n_rec + gridDim.x - 1) / gridDim.x;
     int64_t k0 = (int64_t)blockIdx.x * per, k1 = k0 + per < a.n_rec ? k0 + per : a.n_rec;
+    // endpoints of reads this rank owns never leave it (raftgpu_accumulate_local scatters them directly)
+    const int64_t own_lo = a.own_first, own_hi = a.own_first + a.own_count;
     // pass 1: count
     for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
         int q = a.qid[k], t = a.tid[k];
-        atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull);
-        if (!sym && t != q) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
+        if (q < own_lo || q >= own_hi) atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull);
+        if (!sym && t != q && (t < own_lo || t >= own_hi)) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
     }
     __syncthreads();
     if (!PACK) {
@@ -252,12 +254,12 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
     __syncthreads();
     for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
         int q = a.qid[k], t = a.tid[k];
-        {
+        if (q < own_lo || q >= own_hi) {
             int                d = owner_of(bounds, nranks, q);
             unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
             sendbuf[3 * slot] = q; sendbuf[3 * slot + 1] = a.qs[k]; sendbuf[3 * slot + 2] = a.qe[k];
         }
-        if (!sym && t != q) {
+        if (!sym && t != q && (t < own_lo || t >= own_hi)) {
             int                d = owner_of(bounds, nranks, t);
             unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
             sendbuf[3 * slot] = t; sendbuf[3 * slot + 1] = a.ts[k]; sendbuf[3 * slot + 2] = a.te[k];

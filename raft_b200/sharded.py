@@ -7,8 +7,9 @@ coverage is per read.  Protocol per rank (`run_rank`):
   1. every rank tokenises its byte range of the PAF (split at newlines) against the full name table;
   2. record 0 of the whole file (chop.hpp:171-184 compares every later record with it) is taken from
      the first rank that has a record and broadcast; the symmetric flag is the max over ranks;
-  3. every contributing interval becomes a 12-byte endpoint (global read id, start, end) for the
-     rank that owns the read: counts all-to-all, then ONE data all-to-all (NCCL over NVLink);
+  3. intervals on reads the rank owns are scattered locally; every other contributing interval becomes
+     a 12-byte endpoint (global read id, start, end) for the rank that owns the read: counts
+     all-to-all, then ONE data all-to-all (NCCL over NVLink);
   4. each rank accumulates the endpoints it received, finalises its own reads, and the global
      `read=` numbering is fixed by an all-gather of fragment counts (chop.hpp:195,266,319).
 
@@ -77,10 +78,15 @@ class TorchComm:
         osz, isz = [int(c) for c in recv_counts], [int(c) for c in send_counts]
         if self.buf_device == self.device:
             self.dist.all_to_all_single(recv[:n_r], send[:n_s], output_split_sizes=osz, input_split_sizes=isz)
+            if recv.is_cuda:
+                # the library launches on its own stream: the received endpoints must have landed before it reads them
+                self.torch.cuda.current_stream(recv.device).synchronize()
         else:  # staged (tests: gloo collectives with CUDA buffers)
             r = self.torch.empty(max(n_r, 1), dtype=self.torch.int32, device=self.device)
             self.dist.all_to_all_single(r[:n_r], send[:n_s].to(self.device), output_split_sizes=osz, input_split_sizes=isz)
             recv[:n_r].copy_(r[:n_r])
+            if recv.is_cuda:
+                self.torch.cuda.current_stream(recv.device).synchronize()
 
 
 def run_rank(engine, comm, bounds, text, nbytes):
@@ -100,7 +106,8 @@ def run_rank(engine, comm, bounds, text, nbytes):
     # -- symmetric flag: OR over ranks
     sym = int(comm.all_gather_i64([engine.get_symmetric()]).max())
     engine.set_symmetric(sym)
-    # -- route endpoints to the owners of their reads
+    # -- intervals on reads this rank owns are scattered directly; the rest is routed to the owners
+    engine.accumulate_local()
     counts = engine.route_count(bounds)
     recv_counts = comm.all_to_all_counts(counts)
     send = comm.alloc_i32(3 * int(counts.sum()))
@@ -115,7 +122,7 @@ def run_rank(engine, comm, bounds, text, nbytes):
     engine.set_output_base(first_num)
     info = dict(symmetric=sym, sent=int(counts.sum()), received=int(recv_counts.sum()), first_read_num=first_num,
                 n_records_total=int(per_rank[:, 1].sum()), n_fragments_total=int(per_rank[:, 0].sum()),
-                sent_remote=int(counts.sum() - counts[rank]))
+                sent_remote=int(counts.sum()))
     return st, info
 
 
@@ -182,8 +189,11 @@ def bench(a, rank, world, local, log):
         clocks.start()
     ms, st, info, nout = timed(a.steps)
     clk = clocks.stop() if rank == 0 else None
-    launches = ctx.stats().kernel_launches * a.steps
-    fasta_ms = ctx.stats().ms_emit[3]
+    s2 = ctx.stats()
+    launches = s2.kernel_launches * a.steps
+    fasta_ms = s2.ms_emit[3]
+    stage = {"set_reads": s2.ms_set_reads, "tokenize": s2.ms_tokenize, "scatter": s2.ms_scatter, "scan": s2.ms_scan, "repeat_cut": s2.ms_repeat_cut,
+             "layout": s2.ms_layout, "emit_cov": s2.ms_emit[0], "emit_rep": s2.ms_emit[1], "emit_fasta": s2.ms_emit[3]}
     tot = comm.all_gather_i64([info["sent_remote"], nout, int(own_seq.numel()), int(ds.paf.numel()), launches])
     e2e = None
     if not a.no_e2e:
@@ -216,7 +226,7 @@ def bench(a, rank, world, local, log):
                           "exchange": {"endpoints_sent_to_other_ranks": int(tot[:, 0].sum()), "bytes": 12 * int(tot[:, 0].sum()),
                                        "collective": "all_to_all_single (NCCL) of 12-byte endpoints + counts"},
                           "l2": "inputs and outputs are GBs per rank (>> 126 MB L2); no explicit flush"},
-               "gbp_per_s": int(tot[:, 2].sum()) / (ms / 1e3) / 1e9,
+               "gbp_per_s": int(tot[:, 2].sum()) / (ms / 1e3) / 1e9, "stage_ms_rank0": stage,
                "roofline": {"kernel": "k_fasta_emit", "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
                             "achieved": None if not fasta_ms else 2.0 * nout * 0.98 / (fasta_ms / 1e3) / 1e9,
                             "frac": None if not fasta_ms else 2.0 * nout * 0.98 / (fasta_ms / 1e3) / 1e9 / peak,

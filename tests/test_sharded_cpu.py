@@ -57,13 +57,21 @@ class NumpyEngine:
     def set_symmetric(self, f):
         self.sym = f
 
-    def _endpoints(self):
+    def _all_endpoints(self):
         r = self.r
         e = [np.stack([r.qid, r.qs, r.qe], 1)]
         if not self.sym:
             k = r.tid != r.qid
             e.append(np.stack([r.tid[k], r.ts[k], r.te[k]], 1))
         return np.concatenate(e).astype(np.int32)
+
+    def _endpoints(self):  # the ones that must travel
+        e = self._all_endpoints()
+        return e[(e[:, 0] < self.b0) | (e[:, 0] >= self.b1)]
+
+    def accumulate_local(self):
+        e = self._all_endpoints()
+        self.local_ep = e[(e[:, 0] >= self.b0) & (e[:, 0] < self.b1)]
 
     def route_count(self, bounds):
         e = self._endpoints()
@@ -77,7 +85,7 @@ class NumpyEngine:
         sendbuf[:e.size] = torch.from_numpy(e.reshape(-1).copy())
 
     def accumulate_endpoints(self, recv, count):
-        self.ep = recv[:3 * count].numpy().reshape(-1, 3).copy()
+        self.ep = np.concatenate([self.local_ep, recv[:3 * count].numpy().reshape(-1, 3)])
 
     def finalize(self):
         # coverage of the owned reads from the routed endpoints: feed them back to the oracle as self-overlaps
