@@ -105,6 +105,14 @@ const char *raftgpu_strerror(int status);
 const char *raftgpu_last_error(const raftgpu_ctx *ctx);           /* detail of the last failure (e.g. CUDA error string) */
 int64_t     raftgpu_error_index(const raftgpu_ctx *ctx);          /* record / read index the last data error points at, or -1 */
 
+/* Options (raftgpu_set_option).
+ * RAFTGPU_OPT_DEFER_SEQ_UPLOAD (default 0): with 1, a HOST `seq` passed to raftgpu_set_reads[_sharded] is not
+ * copied inside that call; it is uploaded in chunks on a copy stream once the PAF is complete, overlapping the
+ * kernels and the device->host transfer of the outputs (PCIe full duplex).  The host buffer must then stay valid
+ * (and should be pinned) until the reads.fasta bytes have been fetched, or raftgpu_reset / raftgpu_destroy. */
+enum { RAFTGPU_OPT_DEFER_SEQ_UPLOAD = 1 };
+int raftgpu_set_option(raftgpu_ctx *ctx, int option, int64_t value);
+
 /* ---- a0: reads.  Replaces loadFASTA + addStringToMap (chop.hpp:73-131) once the FASTA is tokenised.
  * seq_off/name_off have n+1 entries; names are the header up to the first whitespace (kseq.h:254);
  * ids are the array order (chop.hpp:108).  seq may be NULL (lengths only: tables and coverage /

@@ -12,6 +12,7 @@ import numpy as np
 from . import _lib
 
 OUT_COVERAGE, OUT_LONG_REPEATS, OUT_BED, OUT_READS_FASTA = 0, 1, 2, 3
+OPT_DEFER_SEQ_UPLOAD = 1
 OUT_SUFFIX = {OUT_COVERAGE: "coverage.txt", OUT_LONG_REPEATS: "long_repeats.txt", OUT_BED: "long_repeats.bed",
               OUT_READS_FASTA: "reads.fasta"}
 (TAB_QID, TAB_TID, TAB_QS, TAB_QE, TAB_TS, TAB_TE, TAB_STRAND, TAB_BIN_OFF, TAB_COV, TAB_REP_OFF, TAB_REP,
@@ -104,6 +105,9 @@ class Context:
     def _ck(self, st):
         if st:
             raise RaftError(st, self.L.raftgpu_last_error(self._h).decode(), self.L.raftgpu_error_index(self._h))
+
+    def set_option(self, option, value):
+        self._ck(self.L.raftgpu_set_option(self._h, option, int(value)))
 
     # ---- a0 loadFASTA (chop.hpp:88-131), after tokenisation
     def set_reads(self, seq_off, seq, name_off, names):

@@ -107,7 +107,20 @@ struct raftgpu_ctx {
     cudaEvent_t ev_emit[2]{};
     bool        emit_pending = false;
     int         emit_pending_which = 0;
+
+    // deferred sequence upload (RAFTGPU_OPT_DEFER_SEQ_UPLOAD)
+    bool           opt_defer_seq = false;
+    cudaStream_t   st_h2d = nullptr;
+    const uint8_t* seq_host = nullptr;   // pending host arena
+    size_t         seq_host_bytes = 0;
+    bool           seq_upload_started = false;
+    std::vector<cudaEvent_t> ev_chunk;   // one per uploaded chunk
+    size_t         n_chunks = 0;
+    std::vector<int64_t> h_frag_sample;  // (out_off, src_off) of every FRAG_SAMPLE-th record
+    DevBuf         b_frag_sample;
 };
+constexpr size_t SEQ_CHUNK = 256ull << 20;
+constexpr int    FRAG_SAMPLE = 256;
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -186,6 +199,7 @@ int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_emit) if (cudaEventCreate(&e) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (ctx->b_misc.ensure(sizeof(Misc)) != cudaSuccess) return bail();
     *out = ctx;
     return raftgpu_reset(ctx);
@@ -199,6 +213,8 @@ int raftgpu_destroy(raftgpu_ctx* ctx)
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_emit) if (e) cudaEventDestroy(e);
+    if (ctx->st_h2d) { cudaStreamSynchronize(ctx->st_h2d); cudaStreamDestroy(ctx->st_h2d); }
+    for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
     delete ctx;
     return RAFTGPU_OK;
@@ -208,6 +224,8 @@ int raftgpu_reset(raftgpu_ctx* ctx)
 {
     if (!ctx) return RAFTGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->st_h2d) CK(cudaStreamSynchronize(ctx->st_h2d)); // an upload in flight still reads the caller's host arena
+    ctx->seq_host = nullptr; ctx->seq_host_bytes = 0; ctx->seq_upload_started = false; ctx->n_chunks = 0;
     Misc h{};
     h.err.index = LLONG_MAX;
     CK(cudaMemcpyAsync(ctx->b_misc.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->st));
@@ -249,6 +267,48 @@ static int adopt(raftgpu_ctx* ctx, DevBuf& buf, const T* src, size_t count, cons
     if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyDefault, ctx->st));
     CK(cudaMemsetAsync((uint8_t*)buf.p + bytes, 0, pad_bytes, ctx->st));
     *out = buf.as<T>();
+    return RAFTGPU_OK;
+}
+
+// sequence arena: device pointers are borrowed, host pointers are copied now or (option) uploaded later in chunks
+static int adopt_seq(raftgpu_ctx* ctx, const uint8_t* seq, size_t bytes)
+{
+    if (!ctx->opt_defer_seq || is_device_ptr(seq) || bytes == 0) return adopt(ctx, ctx->b_seq, seq, bytes, &ctx->d_seq);
+    CK(ctx->b_seq.ensure(bytes + 32));
+    CK(cudaMemsetAsync((uint8_t*)ctx->b_seq.p + bytes, 0, 32, ctx->st));
+    ctx->d_seq = ctx->b_seq.as<uint8_t>();
+    ctx->seq_host = seq; ctx->seq_host_bytes = bytes; ctx->seq_upload_started = false;
+    return RAFTGPU_OK;
+}
+
+// enqueue the chunked upload of a deferred host arena on the copy stream (no-op otherwise)
+static int start_seq_upload(raftgpu_ctx* ctx)
+{
+    if (!ctx->seq_host || ctx->seq_upload_started) return RAFTGPU_OK;
+    ctx->n_chunks = (ctx->seq_host_bytes + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    while (ctx->ev_chunk.size() < ctx->n_chunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_chunk.push_back(e);
+    }
+    for (size_t c = 0; c < ctx->n_chunks; c++) {
+        size_t off = c * SEQ_CHUNK, len = std::min(SEQ_CHUNK, ctx->seq_host_bytes - off);
+        CK(cudaMemcpyAsync((uint8_t*)ctx->b_seq.p + off, ctx->seq_host + off, len, cudaMemcpyHostToDevice, ctx->st_h2d));
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st_h2d));
+    }
+    ctx->seq_upload_started = true;
+    return RAFTGPU_OK;
+}
+
+// make stream `st` wait until arena bytes [0, need_end) have arrived
+static int wait_seq_bytes(raftgpu_ctx* ctx, int64_t need_end, cudaStream_t st)
+{
+    if (!ctx->seq_host) return RAFTGPU_OK;
+    int rc = start_seq_upload(ctx);
+    if (rc) return rc;
+    if (need_end <= 0 || ctx->n_chunks == 0) return RAFTGPU_OK;
+    size_t c = std::min<size_t>(ctx->n_chunks - 1, (size_t)((need_end - 1) / (int64_t)SEQ_CHUNK));
+    CK(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
     return RAFTGPU_OK;
 }
 
@@ -327,7 +387,7 @@ extern "C" int raftgpu_set_reads(raftgpu_ctx* ctx, int64_t n, const int64_t* seq
     if ((st = adopt(ctx, ctx->b_names, names, (size_t)name_bytes, &ctx->d_names))) return st;
     if ((st = adopt(ctx, ctx->b_seq_off, seq_off, (size_t)n + 1, &ctx->d_seq_off))) return st;
     ctx->have_seq = seq != nullptr || seq_bytes == 0;
-    if (seq) { if ((st = adopt(ctx, ctx->b_seq, seq, (size_t)seq_bytes, &ctx->d_seq))) return st; }
+    if (seq) { if ((st = adopt_seq(ctx, seq, (size_t)seq_bytes))) return st; }
     else ctx->d_seq = nullptr;
     std::string first;
     if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
@@ -366,7 +426,7 @@ extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int6
         ctx->d_seq_off = ctx->b_seq_off.as<int64_t>();
     }
     ctx->have_seq = own_seq != nullptr || seq_bytes == 0;
-    if (own_seq) { if ((st = adopt(ctx, ctx->b_seq, own_seq, (size_t)seq_bytes, &ctx->d_seq))) return st; }
+    if (own_seq) { if ((st = adopt_seq(ctx, own_seq, (size_t)seq_bytes))) return st; }
     else ctx->d_seq = nullptr;
     std::string first;
     if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
@@ -465,7 +525,10 @@ extern "C" int raftgpu_ingest_paf(raftgpu_ctx* ctx, const uint8_t* text, size_t 
     }
     int st = tokenize_device(ctx, dtext, (int64_t)proc);
     if (st) return st;
-    if (last_chunk) ctx->paf_done = true;
+    if (last_chunk) {
+        ctx->paf_done = true;
+        if ((st = start_seq_upload(ctx))) return st; // PAF is on the device: the arena upload can overlap everything that follows
+    }
     cudaEventRecord(ctx->ev[1], ctx->st);
     CK(cudaStreamSynchronize(ctx->st));
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -756,6 +819,14 @@ static int layout_outputs(raftgpu_ctx* ctx)
     launch_frag_desc(ctx->b_frag_read.as<int32_t>(), ctx->b_frag_a.as<int32_t>(), ctx->b_frag_b.as<int32_t>(), ctx->b_frag_size.as<int32_t>(),
                      ctx->b_frag_off.as<int64_t>(), ctx->d_seq_off, G, ctx->b_frag_desc.as<FragDesc>(), ctx->st);
     CKL();
+    if (ctx->seq_host) { // coarse output-offset -> arena-offset map for the chunked upload
+        size_t cnt = (size_t)(G / FRAG_SAMPLE + 1);
+        CK(ctx->b_frag_sample.ensure(sizeof(int64_t) * 2 * cnt));
+        launch_frag_sample(ctx->b_frag_desc.as<FragDesc>(), G, FRAG_SAMPLE, ctx->b_frag_sample.as<int64_t>(), ctx->st);
+        CKL();
+        ctx->h_frag_sample.resize(2 * cnt);
+        CK(cudaMemcpyAsync(ctx->h_frag_sample.data(), ctx->b_frag_sample.p, sizeof(int64_t) * 2 * cnt, cudaMemcpyDeviceToHost, ctx->st));
+    }
     cudaEventRecord(ctx->ev[7], ctx->st);
     CK(cudaStreamSynchronize(ctx->st));
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); s.ms_layout = ms;
@@ -840,6 +911,17 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
     } else if (which == RAFTGPU_OUT_READS_FASTA) {
         if (!ctx->have_seq) FAIL(RAFTGPU_E_STATE, "reads.fasta requested but no sequence bytes were given");
         if (!ctx->real_reads) FAIL(RAFTGPU_E_UNSUPPORTED, "simulated-read headers (chop.hpp:252-258,293-310) are not emitted by the device path");
+        if (ctx->seq_host) {
+            // arena bytes needed by stream window [w0, w1): records are in arena order, consecutive records of a
+            // read overlap by at most overlap_length bytes
+            int64_t need = (int64_t)ctx->seq_host_bytes;
+            const auto& sm = ctx->h_frag_sample;
+            size_t lo = 0, hi = sm.size() / 2; // first sample with out_off >= w1
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if (sm[2 * mid] >= w1) hi = mid; else lo = mid + 1; }
+            if (lo < sm.size() / 2) need = std::min<int64_t>(need, sm[2 * lo + 1] + std::max(0, ctx->prm.overlap_length) + 64);
+            int rc = wait_seq_bytes(ctx, need, st);
+            if (rc) return rc;
+        }
         FastaEmitArgs fa{};
         fa.desc = ctx->b_frag_desc.as<FragDesc>(); fa.G = ctx->G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
         fa.names = ctx->d_names; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first; fa.read_num_base = ctx->read_num_base;
@@ -850,6 +932,13 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         CKL();
     }
     return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_set_option(raftgpu_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (option == RAFTGPU_OPT_DEFER_SEQ_UPLOAD) { ctx->opt_defer_seq = value != 0; return RAFTGPU_OK; }
+    return RAFTGPU_E_ARG;
 }
 
 extern "C" int raftgpu_get_stats(raftgpu_ctx* ctx, raftgpu_stats* out)

@@ -308,6 +308,19 @@ void launch_frag_desc(const int32_t* frag_read, const int32_t* frag_a, const int
     k_frag_desc<<<(unsigned)((G + 1 + 255) / 256), 256, 0, st>>>(frag_read, frag_a, frag_b, frag_size, frag_off, seq_off, G, desc);
 }
 
+__global__ void k_frag_sample(const FragDesc* __restrict__ desc, int64_t G, int step, int64_t* out2)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t g = k * step;
+    if (g > G) return;
+    out2[2 * k] = desc[g].out_off; out2[2 * k + 1] = desc[g].src_off;
+}
+void launch_frag_sample(const FragDesc* desc, int64_t G, int step, int64_t* out2, cudaStream_t st)
+{
+    int64_t cnt = G / step + 1;
+    k_frag_sample<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(desc, G, step, out2);
+}
+
 __global__ void __launch_bounds__(FE_THREADS, 5) k_fasta_emit(FastaEmitArgs a)
 {
     extern __shared__ __align__(16) uint8_t fe_raw[];

@@ -159,6 +159,8 @@ struct __align__(32) FragDesc {
 };
 void launch_frag_desc(const int32_t* frag_read, const int32_t* frag_a, const int32_t* frag_b, const int32_t* frag_size, const int64_t* frag_off,
                       const int64_t* seq_off, int64_t G, FragDesc* desc, cudaStream_t st);
+// every `step`-th record's (out_off, src_off): a coarse host-side map from output offset to arena offset
+void launch_frag_sample(const FragDesc* desc, int64_t G, int step, int64_t* out2, cudaStream_t st);
 struct FastaEmitArgs {
     const FragDesc* desc;    // G+1 (last: out_off = stream length)
     int64_t        G;

@@ -264,3 +264,28 @@ def test_many_tiny_reads_and_fragments():
     ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
     compare_all(ctx, st, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_deferred_sequence_upload(pinned):
+    """RAFTGPU_OPT_DEFER_SEQ_UPLOAD: the arena is uploaded in chunks behind the PAF; windows wait for their chunks."""
+    torch = pytest.importorskip("torch")
+    ds = synth.make_dataset("C2", 0.0006, True, seed=21)
+    p = api.AlgoParams.from_args(ds.args)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    seq = np.ascontiguousarray(ds.reads.seq, np.uint8)
+    if pinned:
+        seq = torch.from_numpy(seq.copy()).pin_memory().numpy()
+    ctx = api.Context(p)
+    ctx.set_option(api.OPT_DEFER_SEQ_UPLOAD, 1)
+    for rep in range(2):  # second pass: reset while nothing is pending, reuse of chunk events
+        ctx.set_reads(np.ascontiguousarray(ds.reads.seq_off, np.int64), seq, np.ascontiguousarray(ds.reads.name_off, np.int64),
+                      np.ascontiguousarray(ds.reads.names, np.uint8))
+        ctx.ingest_paf(np.frombuffer(ds.paf, np.uint8), len(ds.paf), last=True)
+        ctx.run()
+        total = ctx.output_size(api.OUT_READS_FASTA)
+        assert ctx.fetch(api.OUT_READS_FASTA, total - 1000, 1000) == ref.fasta[-1000:]   # a late window first
+        assert ctx.fetch(api.OUT_READS_FASTA) == ref.fasta
+        assert ctx.fetch(api.OUT_COVERAGE) == ref.cov_txt
+        assert ctx.digest(api.OUT_READS_FASTA) == O.digest(ref.fasta)
+    ctx.close()
