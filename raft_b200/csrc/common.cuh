@@ -179,6 +179,12 @@ __device__ __forceinline__ uint8_t dec_digit_at(uint64_t v, int nd, int k)
     return (uint8_t)('0' + (uint32_t)(v % 10ull));
 }
 
+__device__ __forceinline__ uint8_t dec_digit_at32(uint32_t v, int nd, int k)
+{
+    for (int i = nd - 1 - k; i > 0; --i) v /= 10u;
+    return (uint8_t)('0' + (v % 10u));
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
@@ -223,6 +229,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "bra WAIT_LOOP;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // dst (shared, 16B aligned), src (global, 16B aligned), bytes multiple of 16
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)

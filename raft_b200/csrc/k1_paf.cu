@@ -33,28 +33,29 @@ constexpr int K1_STAGE = K1_TILE + K1_OVER;
 constexpr int K1_WORDS = K1_STAGE / 32;    // 544 mask words over the staged bytes
 constexpr int K1_TWORDS = K1_TILE / 32;    // 512: line starts live in bits [0, TILE] -> words [0, 512]
 
+constexpr int K1_MAXREC = K1_TILE / 10 + 2; // a record has >= 9 tabs + newline: at most 1639 start in a tile
+
 struct __align__(16) K1Smem {
     uint8_t  text[K1_STAGE + 16];
-    unsigned nl[K1_WORDS];    // byte is '\n'
-    unsigned tab[K1_WORDS];   // byte is '\t'
-    unsigned ls[K1_WORDS];    // a non-empty line owned by this tile starts at this byte
-    unsigned valid[K1_WORDS]; // ... and it is a record (>= 9 tabs)
-    uint16_t vpre[K1_WORDS + 2]; // records before word w
+    unsigned nl[K1_WORDS + 1];    // byte is '\n'   (+1: all-ones sentinel word)
+    unsigned tab[K1_WORDS + 1];   // byte is '\t'   (+1: all-ones sentinel word)
+    uint16_t vpos[K1_MAXREC];     // start of the j-th record of the tile, tile relative
     uint64_t bar;
     uint64_t bcast;
     int      scan_ws[34];
     int      tile;
 };
 
-// bit k set iff byte k of the 16-byte group equals c
+// bit k set iff byte k of the 16-byte group equals c (c4 = c in every byte).  Exact per-byte zero test on
+// v ^ c4 (0x80 per equal byte), then two unsigned dp4a per 8 bytes gather the flags: sum(128 * 2^i).
+__device__ __forceinline__ unsigned zero_flags(unsigned x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
 __device__ __forceinline__ unsigned eq_mask16(const uint4& v, unsigned c4)
 {
-    auto m4 = [&](unsigned w) -> unsigned {
-        unsigned x = __vcmpeq4(w, c4);                 // 0xFF per equal byte
-        x &= 0x01010101u;                              // bit 0 of each byte
-        return ((x * 0x01020408u) >> 24) & 0xFu;       // gather to 4 bits (byte i -> bit i)
-    };
-    return m4(v.x) | (m4(v.y) << 4) | (m4(v.z) << 8) | (m4(v.w) << 12);
+    unsigned lo = __dp4a(zero_flags(v.x ^ c4), 0x08040201u, 0u);
+    lo = __dp4a(zero_flags(v.y ^ c4), 0x80402010u, lo);
+    unsigned hi = __dp4a(zero_flags(v.z ^ c4), 0x08040201u, 0u);
+    hi = __dp4a(zero_flags(v.w ^ c4), 0x80402010u, hi);
+    return (lo >> 7) | ((hi >> 7) << 8);
 }
 
 // Byte reader over the text: staged bytes come from shared memory (32-bit word cache), the rest
@@ -158,13 +159,12 @@ __device__ __forceinline__ void report_error(ErrState* err, int code, long long 
     if (index <= old) err->code = code;
 }
 
-// first set bit of mask m at position >= from (bit index over K1_WORDS words), or K1_STAGE
+// first set bit of mask m at position >= from; the sentinel word makes it return >= K1_STAGE when there is none
 __device__ __forceinline__ int next_bit(const unsigned* m, int from)
 {
-    if (from >= K1_STAGE) return K1_STAGE;
     int      w = from >> 5;
     unsigned x = m[w] & (0xFFFFFFFFu << (from & 31));
-    while (!x) { if (++w >= K1_WORDS) return K1_STAGE; x = m[w]; }
+    while (!x) x = m[++w];
     return (w << 5) + __ffs(x) - 1;
 }
 // number of set bits of m in [from, to)
@@ -200,53 +200,27 @@ __device__ __forceinline__ int parse_num_smem(const uint8_t* s, int a, int b)
 // hash of staged bytes [a, b): same value as NameHasher fed byte by byte
 __device__ __forceinline__ unsigned long long hash_name_smem(const unsigned* sw, int a, int b, unsigned long long seed)
 {
-    unsigned long long h = seed ^ 0x9E3779B97F4A7C15ull;
-    const int          n = b - a;
-    int                wi = a >> 2;
-    const unsigned     sh = (unsigned)(a & 3) * 8u;
-    unsigned           lo = sw[wi];
-    int                k = 0;
+    NameHasher hs;
+    hs.init(seed);
+    const int      n = b - a;
+    int            wi = a >> 2;
+    const unsigned sh = (unsigned)(a & 3) * 8u;
+    unsigned       lo = sw[wi];
+    int            k = 0;
     for (; k + 4 <= n; k += 4) {
         unsigned hi = sw[++wi];
-        unsigned w = __funnelshift_r(lo, hi, sh);
+        hs.word(__funnelshift_r(lo, hi, sh));
         lo = hi;
-        h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
     }
     const int rem = n - k;
     if (rem) {
         unsigned hi = sw[wi + 1];
-        unsigned w = __funnelshift_r(lo, hi, sh) & ((1u << (8 * rem)) - 1u);
-        h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+        hs.word(__funnelshift_r(lo, hi, sh) & ((1u << (8 * rem)) - 1u));
     }
-    unsigned long long r = mix64(h ^ ((unsigned long long)(unsigned)n << 32));
-    return r ? r : 1ull;
+    return name_hash_finish(hs.a, hs.b, (unsigned)n);
 }
 
-// position of the j-th set bit of a mask given its per-word exclusive prefix counts (pre has K1_TWORDS+2 entries)
-__device__ __forceinline__ int select_bit(const unsigned* m, const uint16_t* pre, int j)
-{
-    int lo = 0, hi = K1_TWORDS + 1;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)pre[mid] <= j) lo = mid; else hi = mid; }
-    unsigned v = m[lo];
-    for (int k = j - (int)pre[lo]; k > 0; k--) v &= v - 1;
-    return (lo << 5) + __ffs(v) - 1;
-}
-
-// exclusive prefix of popc over mask words [0, K1_TWORDS] -> pre[0..K1_TWORDS+1]; returns the total.  Block-wide.
-__device__ __forceinline__ int mask_prefix(const unsigned* m, uint16_t* pre, int* scan_ws)
-{
-    const int tid = threadIdx.x;
-    const int wlo = tid * 2, whi = (tid == K1_THREADS - 1) ? K1_TWORDS + 1 : wlo + 2;
-    int       mine = 0;
-    for (int w = wlo; w < whi; w++) mine += __popc(m[w]);
-    int tot;
-    int run = block_exclusive_sum<int, K1_THREADS>(mine, scan_ws, &tot);
-    for (int w = wlo; w < whi; w++) { pre[w] = (uint16_t)run; run += __popc(m[w]); }
-    if (tid == K1_THREADS - 1) pre[K1_TWORDS + 1] = (uint16_t)run;
-    return tot;
-}
-
-__global__ void __launch_bounds__(K1_THREADS) k_paf_tokenize(PafTokArgs a)
+__global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
@@ -280,100 +254,99 @@ __global__ void __launch_bounds__(K1_THREADS) k_paf_tokenize(PafTokArgs a)
         unsigned pn = __shfl_down_sync(FULL, mn, 1), pt = __shfl_down_sync(FULL, mt, 1);
         if (!(lane & 1)) { s.nl[g >> 1] = mn | (pn << 16); s.tab[g >> 1] = mt | (pt << 16); }
     }
-    __syncthreads();
-    // ---- line starts: byte p starts a non-empty line iff byte p-1 is '\n' (owned: p-1 inside the tile) and byte p is not
-    for (int w = tid; w < K1_WORDS; w += K1_THREADS) {
-        unsigned m = 0;
-        if (w <= K1_TWORDS) {
-            unsigned prev = w ? (s.nl[w - 1] >> 31) : ((tile == 0) ? 1u : 0u); // the file's first byte starts a line
-            m = ((s.nl[w] << 1) | prev) & ~s.nl[w];
-            if (w == K1_TWORDS) m &= 1u;
-        }
-        s.ls[w] = m;
-        s.valid[w] = 0;
-    }
-    __syncthreads();
-    const int n_lines = mask_prefix(s.ls, s.vpre, s.scan_ws); // vpre: line-start prefix for now
+    if (tid == 0) { s.nl[K1_WORDS] = 0xFFFFFFFFu; s.tab[K1_WORDS] = 0xFFFFFFFFu; }
     __syncthreads();
 
     TextReader rd;
     rd.text = a.text; rd.nbytes = a.nbytes; rd.stage_lo = 0; rd.stage_len = 0; rd.swords = nullptr; rd.word = 0;
 
-    // ---- phase A: one thread per line: a record iff >= 9 tabs before its newline (paf.hpp:84)
-    for (int j = tid; j < n_lines; j += K1_THREADS) {
-        int p = select_bit(s.ls, s.vpre, j);
-        int e = next_bit(s.nl, p);                 // the line's newline, or K1_STAGE when it is not staged
-        int tabs = count_bits(s.tab, p, e);
-        if (tabs < 9 && e == K1_STAGE && t0 + K1_STAGE < a.nbytes) { // runs past the staged bytes: read on
-            rd.seek(t0 + K1_STAGE);
-            for (;;) { int c = rd.next(); if (c < 0 || c == '\n') break; if (c == '\t' && ++tabs >= 9) break; }
+    // ---- phase A: thread t owns mask words 2t, 2t+1 (thread 255 also word 512).  A byte p starts a non-empty line
+    // owned by this tile iff byte p-1 is '\n' inside the tile and byte p is not; the line is a record iff it has
+    // >= 9 tabs before its newline (paf.hpp:84).
+    const int wlo = tid * 2, whi = (tid == K1_THREADS - 1) ? K1_TWORDS + 1 : wlo + 2;
+    unsigned  vmask[3] = {0, 0, 0};
+    int       my_valid = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int w = wlo + i;
+        if (w >= whi) break;
+        unsigned prev = w ? (s.nl[w - 1] >> 31) : ((tile == 0) ? 1u : 0u); // the file's first byte starts a line
+        unsigned m = ((s.nl[w] << 1) | prev) & ~s.nl[w];
+        if (w == K1_TWORDS) m &= 1u;
+        unsigned v = 0;
+        while (m) {
+            int bit = __ffs(m) - 1; m &= m - 1;
+            int p = (w << 5) + bit;
+            int e = next_bit(s.nl, p);                 // the line's newline (>= K1_STAGE when it is not staged)
+            if (e > K1_STAGE) e = K1_STAGE;
+            int tabs = count_bits(s.tab, p, e);
+            if (tabs < 9 && e == K1_STAGE && t0 + K1_STAGE < a.nbytes) { // runs past the staged bytes: read on
+                rd.seek(t0 + K1_STAGE);
+                for (;;) { int c = rd.next(); if (c < 0 || c == '\n') break; if (c == '\t' && ++tabs >= 9) break; }
+            }
+            if (tabs >= 9) v |= 1u << bit;
         }
-        if (tabs >= 9) atomicOr(&s.valid[p >> 5], 1u << (p & 31));
+        vmask[i] = v;
+        my_valid += __popc(v);
     }
-    __syncthreads();
-    const int n_valid = mask_prefix(s.valid, s.vpre, s.scan_ws); // vpre: record prefix from here on
-    if (tid == 0) {
-        lookback_publish(a.status, tile, (uint64_t)n_valid);     // successors can look back while this tile decodes
+    int n_valid;
+    int ex = block_exclusive_sum<int, K1_THREADS>(my_valid, s.scan_ws, &n_valid);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        unsigned v = vmask[i];
+        while (v) { int bit = __ffs(v) - 1; v &= v - 1; s.vpos[ex++] = (uint16_t)(((wlo + i) << 5) + bit); }
     }
+    if (tid == 0) lookback_publish(a.status, tile, (uint64_t)n_valid); // successors can look back while this tile decodes
     __syncthreads();
 
-    // ---- phase B: decode.  Two threads per record when the tile's records fit (even lane: query side, odd lane: target side)
+    // ---- phase B: decode the j-th record of the tile, one per thread
     int r0[7];
 #pragma unroll
     for (int k = 0; k < 7; k++) r0[k] = a.rec0[k];
     const unsigned* sw = reinterpret_cast<const unsigned*>(s.text);
-    const bool      pair = n_valid * 2 <= K1_THREADS;
-    const int       per_round = pair ? K1_THREADS / 2 : K1_THREADS;
     uint64_t        prefix = 0;
     bool            have_prefix = false;
-    for (int base = 0; base < n_valid || !have_prefix; base += per_round) {
-        const int  j = base + (pair ? (tid >> 1) : tid);
+    for (int base = 0; base < n_valid || !have_prefix; base += K1_THREADS) {
+        const int  j = base + tid;
         const bool active = j < n_valid;
-        const bool doA = active && (!pair || !(tid & 1)), doB = active && (!pair || (tid & 1));
-        int  p = 0, t4 = 0, qid = 0, tidv = 0, qs = 0, qe = 0, ts = 0, te = 0;
-        unsigned strand = 0;
-        bool staged = true;
-        if (active) p = select_bit(s.valid, s.vpre, j);
-        if (doA) {
-            int t0_ = next_bit(s.tab, p), t1 = next_bit(s.tab, t0_ + 1), t2 = next_bit(s.tab, t1 + 1), t3 = next_bit(s.tab, t2 + 1);
-            t4 = next_bit(s.tab, t3 + 1);
-            if (t4 < K1_STAGE) {
-                qid = nametable_find(a.names, hash_name_smem(sw, p, t0_, a.names.seed));
-                qs = parse_num_smem(s.text, t1 + 1, t2); qe = parse_num_smem(s.text, t2 + 1, t3);
-                strand = (t4 > t3 + 1) && s.text[t3 + 1] == '-';
-            } else staged = false;
-        }
-        if (pair) t4 = __shfl_sync(FULL, t4, lane & ~1);
-        if (doB) {
-            if (t4 < K1_STAGE) {
-                int t5 = next_bit(s.tab, t4 + 1), t6 = next_bit(s.tab, t5 + 1), t7 = next_bit(s.tab, t6 + 1), t8 = next_bit(s.tab, t7 + 1);
-                if (t8 < K1_STAGE) {
-                    tidv = nametable_find(a.names, hash_name_smem(sw, t4 + 1, t5, a.names.seed));
-                    ts = parse_num_smem(s.text, t6 + 1, t7); te = parse_num_smem(s.text, t7 + 1, t8);
-                } else staged = false;
-            } else staged = false;
-        }
-        if (pair) staged = __shfl_sync(FULL, (int)staged, lane & ~1) && __shfl_sync(FULL, (int)staged, lane | 1);
-        if (active && !staged) { // the record runs past the staged bytes: byte-wise reader over global memory (both lanes of a pair)
-            ParsedRec pr;
-            rd.seek(t0 + p);
-            parse_record(rd, a.names, pr);
-            qid = pr.qid; tidv = pr.tid; qs = pr.qs; qe = pr.qe; ts = pr.ts; te = pr.te; strand = pr.strand;
+        ParsedRec  pr;
+        pr.qid = pr.tid = pr.qs = pr.qe = pr.ts = pr.te = 0; pr.strand = 0;
+        int p = 0;
+        if (active) {
+            p = s.vpos[j];
+            // the nine tabs that end fields 0..8: walk the tab mask word by word
+            int      tp[9];
+            int      w = p >> 5;
+            unsigned cur = s.tab[w] & (0xFFFFFFFFu << (p & 31));
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                while (!cur) cur = s.tab[++w];
+                tp[k] = (w << 5) + __ffs(cur) - 1;
+                cur &= cur - 1;
+            }
+            if (tp[8] < K1_STAGE) {
+                pr.qid = nametable_find(a.names, hash_name_smem(sw, p, tp[0], a.names.seed));
+                pr.tid = nametable_find(a.names, hash_name_smem(sw, tp[4] + 1, tp[5], a.names.seed));
+                pr.qs = parse_num_smem(s.text, tp[1] + 1, tp[2]); pr.qe = parse_num_smem(s.text, tp[2] + 1, tp[3]);
+                pr.strand = (tp[4] > tp[3] + 1) && s.text[tp[3] + 1] == '-';
+                pr.ts = parse_num_smem(s.text, tp[6] + 1, tp[7]); pr.te = parse_num_smem(s.text, tp[7] + 1, tp[8]);
+            } else { // the record runs past the staged bytes: byte-wise reader over global memory
+                rd.seek(t0 + p);
+                parse_record(rd, a.names, pr);
+            }
         }
         if (!have_prefix) { prefix = lookback_wait(a.status, tile, (uint64_t)n_valid, &s.bcast); have_prefix = true; }
+        if (!active) continue;
         const int64_t rec = a.rec_base + (int64_t)prefix + j;
-        // symmetric predicate (chop.hpp:171-184): record k >= 1 mirrors record 0; each lane checks its half
-        bool mA = r0[1] == qid && r0[4] == qs && r0[5] == qe, mB = r0[0] == tidv && r0[2] == ts && r0[3] == te;
-        if (pair) { bool oA = __shfl_sync(FULL, (int)mA, lane & ~1), oB = __shfl_sync(FULL, (int)mB, lane | 1); mA = oA; mB = oB; }
-        if (doA) {
-            if (qid < 0) report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec);
-            else if (rec < a.rec_cap) { a.qid[rec] = qid; a.qs[rec] = qs; a.qe[rec] = qe; a.strand[rec] = (uint8_t)strand; }
-            if (r0[6] && (rec != 0 || !a.first_is_local) && mA && mB) *a.sym_flag = 1;
+        if (pr.qid < 0 || pr.tid < 0) { report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec); continue; }
+        if (rec < a.rec_cap) {
+            a.qid[rec] = pr.qid; a.tid[rec] = pr.tid; a.qs[rec] = pr.qs; a.qe[rec] = pr.qe;
+            a.ts[rec] = pr.ts; a.te[rec] = pr.te; a.strand[rec] = (uint8_t)pr.strand;
         }
-        if (doB) {
-            if (tidv < 0) report_error(a.err, RAFTK_E_UNKNOWN_NAME, rec);
-            else if (rec < a.rec_cap) { a.tid[rec] = tidv; a.ts[rec] = ts; a.te[rec] = te; }
-        }
+        // chop.hpp:171-184: record k >= 1 mirrors record 0
+        if (r0[6] && (rec != 0 || !a.first_is_local) && r0[0] == pr.tid && r0[1] == pr.qid && r0[2] == pr.ts &&
+            r0[3] == pr.te && r0[4] == pr.qs && r0[5] == pr.qe)
+            *a.sym_flag = 1;
     }
     if (tid == 0 && tile == a.n_tiles - 1) *a.n_records_out = a.rec_base + (int64_t)prefix + n_valid;
 }

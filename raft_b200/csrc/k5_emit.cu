@@ -201,14 +201,20 @@ void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st)
 }
 
 // ================================================================ K5b reads.fasta
-// Output-tile-parallel gather.  CTA b owns stream bytes [T*16Ki, (T+1)*16Ki) of reads.fasta.  One thread
-// walks the records that intersect the tile (tile_frag[T] gives the first) and issues one 1-D TMA bulk
-// copy per sequence piece from the read arena into shared memory (16-byte aligned superset of the
-// piece); all threads then realign from shared memory (two aligned 128-bit shared loads + funnel
-// shifts) and store aligned 128-bit words to the output, and generate the few header bytes directly.
+// Output-tile-parallel gather, persistent and warp-specialised.  A tile is 16 KiB of the reads.fasta stream.
+// Warp 0 (one lane) is the producer: for each tile it walks the records that intersect it (tile_frag[T] gives
+// the first, FragDesc has everything else in one 32-byte load), writes a piece list into the next free
+// pipeline slot and issues one 1-D TMA bulk copy per sequence piece from the read arena into that slot's
+// stage buffer (a 16-byte aligned superset of the piece).  Warps 1..7 are consumers: they wait on the
+// slot's `full` mbarrier (producer arrive + TMA transaction bytes), generate the few header bytes,
+// realign the staged bases (two aligned 128-bit shared loads + funnel shifts) into aligned 128-bit
+// streaming stores, and release the slot through its `empty` mbarrier.  With two slots the walk and the
+// TMA latency of tile i+1 hide behind the stores of tile i.
 constexpr int FE_THREADS = 256;
-constexpr int FE_MAXP = 24;                         // pieces staged per round
-constexpr int FE_STAGE = FASTA_TILE + FE_MAXP * 32; // staged source bytes per round
+constexpr int FE_CONSUMERS = FE_THREADS - 32;       // 7 warps
+constexpr int FE_SLOTS = 2;
+constexpr int FE_MAXP = 24;                         // pieces per slot
+constexpr int FE_STAGE = FASTA_TILE + FE_MAXP * 32; // staged source bytes per slot
 
 struct FePiece {
     long long frag;   // record index
@@ -223,12 +229,11 @@ struct FePiece {
 };
 
 struct __align__(16) FeSmem {
-    uint8_t  stage[FE_STAGE];
-    FePiece  piece[FE_MAXP];
-    uint64_t bar;
-    int      np;
-    int      more;      // records of the tile left for another round
-    long long next_g;
+    uint8_t   stage[FE_SLOTS][FE_STAGE];
+    FePiece   piece[FE_SLOTS][FE_MAXP];
+    long long x0[FE_SLOTS], x1[FE_SLOTS];
+    int       np[FE_SLOTS]; // -1: no more work
+    uint64_t  full[FE_SLOTS], empty[FE_SLOTS];
 };
 
 __device__ __forceinline__ uint4 lds_unaligned16(const uint8_t* sp)
@@ -261,18 +266,18 @@ __device__ __forceinline__ uint4 lds_unaligned16(const uint8_t* sp)
     return o;
 }
 
-// all threads: n bytes from shared memory (any alignment) to global (any alignment)
-__device__ __forceinline__ void block_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n)
+// consumer threads (index ct of FE_CONSUMERS): n bytes from shared memory (any alignment) to global (any alignment)
+__device__ __forceinline__ void consumers_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n, int ct)
 {
     int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
     if (head > n) head = n;
-    for (int k = threadIdx.x; k < head; k += FE_THREADS) dst[k] = sp[k];
+    for (int k = ct; k < head; k += FE_CONSUMERS) dst[k] = sp[k];
     const int nbody = (n - head) >> 4;
     uint4*    d16 = reinterpret_cast<uint4*>(dst + head);
     const uint8_t* s = sp + head;
-    for (int c = threadIdx.x; c < nbody; c += FE_THREADS) stg_stream(d16 + c, lds_unaligned16(s + (c << 4)));
+    for (int c = ct; c < nbody; c += FE_CONSUMERS) stg_stream(d16 + c, lds_unaligned16(s + (c << 4)));
     const int done = head + (nbody << 4);
-    for (int k = done + threadIdx.x; k < n; k += FE_THREADS) dst[k] = sp[k];
+    for (int k = done + ct; k < n; k += FE_CONSUMERS) dst[k] = sp[k];
 }
 
 __global__ void __launch_bounds__(256) k_fasta_tile_index(const int64_t* __restrict__ frag_off, int64_t G, int64_t n_tiles, int32_t* tile_frag)
@@ -321,123 +326,141 @@ void launch_frag_sample(const FragDesc* desc, int64_t G, int step, int64_t* out2
     k_frag_sample<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(desc, G, step, out2);
 }
 
-__global__ void __launch_bounds__(FE_THREADS, 5) k_fasta_emit(FastaEmitArgs a)
+__global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, int64_t n_tiles)
 {
     extern __shared__ __align__(16) uint8_t fe_raw[];
     FeSmem& s = *reinterpret_cast<FeSmem*>(fe_raw);
-    const int64_t T = a.w0 / FASTA_TILE + blockIdx.x;
-    const int64_t xs = T * FASTA_TILE;
-    const int64_t x0 = xs > a.w0 ? xs : a.w0;
-    const int64_t x1 = (xs + FASTA_TILE) < a.w1 ? (xs + FASTA_TILE) : a.w1;
-    if (x0 >= x1) return;
     if (threadIdx.x == 0) {
-        mbar_init(&s.bar, 1);
-        s.next_g = a.tile_frag[T]; // record containing the tile's first byte
+        for (int k = 0; k < FE_SLOTS; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], FE_CONSUMERS / 32); }
     }
     __syncthreads();
-    unsigned phase = 0;
-    for (;;) {
-        // ---- one thread: list the pieces of this round and start their TMA copies
-        if (threadIdx.x == 0) {
-            int     np = 0, used = 0;
-            int64_t g = s.next_g;
-            bool    more = false;
-            for (; g < a.G; g++) {
-                const FragDesc d = a.desc[g];
-                const int64_t  O = d.out_off;
-                if (O >= x1) break;
-                const int64_t s0 = O + d.hdr_len, s1 = s0 + d.len;
-                if (s1 + 1 <= x0) continue;                               // the window starts after this record
-                if (np == FE_MAXP) { more = true; break; }
-                const int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
-                FePiece&      pc = s.piece[np];
-                pc.frag = g; pc.O = O; pc.p0 = p0; pc.n = p1 > p0 ? (int)(p1 - p0) : 0; pc.n_stage = 0; pc.soff = 0; pc.bulk = 0; pc.src = nullptr;
-                pc.h = d.hdr_len; pc.len = d.len; pc.read = d.read; pc.fa = d.a;
-                if (pc.n > 0) {
-                    const int64_t srcoff = d.src_off + (p0 - s0);         // offset in the arena
-                    const int64_t al = srcoff & ~(int64_t)15;
-                    int64_t       end = (srcoff + pc.n + 15) & ~(int64_t)15;
-                    if (end > a.seq_safe_end) end = a.seq_safe_end;       // never read past what the arena guarantees
-                    const int bytes = end > al ? (int)(end - al) : 0;
-                    if (used + bytes > FE_STAGE) { more = true; break; }  // next round
-                    pc.src = a.seq + srcoff;
-                    pc.soff = used + (int)(srcoff - al);
-                    const int avail = bytes - (int)(srcoff - al);
-                    pc.n_stage = avail < 0 ? 0 : (avail > pc.n ? pc.n : avail);
-                    pc.bulk = bytes;
-                    used += bytes;
-                }
-                np++;
-            }
-            s.np = np; s.next_g = g; s.more = more ? 1 : 0;
-            if (used > 0) {
-                mbar_expect_tx(&s.bar, (uint32_t)used);
-                int off = 0;
-                for (int k = 0; k < np; k++) {
-                    const FePiece& pc = s.piece[k];
-                    if (pc.bulk > 0) {
-                        tma_load_1d(s.stage + off, pc.src - (pc.soff - off), (uint32_t)pc.bulk, &s.bar);
-                        off += pc.bulk;
+    const int64_t T0 = a.w0 / FASTA_TILE;
+
+    if (threadIdx.x < 32) {
+        // ================= producer (one lane) =================
+        if (threadIdx.x != 0) return;
+        int      slot = 0;
+        unsigned ph = 0;
+        for (int64_t t = blockIdx.x;; t += gridDim.x) {
+            const bool    done = t >= n_tiles;
+            const int64_t T = T0 + t, xs = T * FASTA_TILE;
+            const int64_t x0 = xs > a.w0 ? xs : a.w0;
+            const int64_t x1 = (xs + FASTA_TILE) < a.w1 ? (xs + FASTA_TILE) : a.w1;
+            int64_t       g = done ? 0 : a.tile_frag[T]; // record containing the tile's first byte
+            bool          more = true;
+            while (more) {
+                mbar_wait(&s.empty[slot], ph ^ 1);   // the consumers are done with this slot's previous contents
+                int np = 0, used = 0;
+                more = false;
+                if (done) {
+                    np = -1;
+                } else {
+                    FePiece* pl = s.piece[slot];
+                    for (; g < a.G; g++) {
+                        const FragDesc d = a.desc[g];
+                        const int64_t  O = d.out_off;
+                        if (O >= x1) break;
+                        const int64_t s0 = O + d.hdr_len, s1 = s0 + d.len;
+                        if (s1 + 1 <= x0) continue;                               // the window starts after this record
+                        if (np == FE_MAXP) { more = true; break; }
+                        const int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
+                        FePiece&      pc = pl[np];
+                        pc.frag = g; pc.O = O; pc.p0 = p0; pc.n = p1 > p0 ? (int)(p1 - p0) : 0; pc.n_stage = 0; pc.soff = 0; pc.bulk = 0; pc.src = nullptr;
+                        pc.h = d.hdr_len; pc.len = d.len; pc.read = d.read; pc.fa = d.a;
+                        if (pc.n > 0) {
+                            const int64_t srcoff = d.src_off + (p0 - s0);         // offset in the arena
+                            const int64_t al = srcoff & ~(int64_t)15;
+                            int64_t       end = (srcoff + pc.n + 15) & ~(int64_t)15;
+                            if (end > a.seq_safe_end) end = a.seq_safe_end;       // never read past what the arena guarantees
+                            const int bytes = end > al ? (int)(end - al) : 0;
+                            if (used + bytes > FE_STAGE) { more = true; break; }  // another slot for the rest of this tile
+                            pc.src = a.seq + srcoff;
+                            pc.soff = used + (int)(srcoff - al);
+                            const int avail = bytes - (int)(srcoff - al);
+                            pc.n_stage = avail < 0 ? 0 : (avail > pc.n ? pc.n : avail);
+                            pc.bulk = bytes;
+                            used += bytes;
+                        }
+                        np++;
                     }
                 }
-            } else {
-                // nothing staged this round: complete the phase by hand so that the wait below falls through
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.bar)) : "memory");
+                s.np[slot] = np; s.x0[slot] = x0; s.x1[slot] = x1;
+                if (used > 0) {
+                    mbar_expect_tx(&s.full[slot], (uint32_t)used); // arrive (release: the list above is visible) + expected bytes
+                    int off = 0;
+                    for (int k = 0; k < np; k++) {
+                        const FePiece& pc = s.piece[slot][k];
+                        if (pc.bulk > 0) {
+                            tma_load_1d(s.stage[slot] + off, pc.src - (pc.soff - off), (uint32_t)pc.bulk, &s.full[slot]);
+                            off += pc.bulk;
+                        }
+                    }
+                } else {
+                    mbar_arrive(&s.full[slot]);
+                }
+                if (++slot == FE_SLOTS) { slot = 0; ph ^= 1; }
             }
+            if (done) break;
         }
-        __syncthreads();
-        // ---- all threads: header bytes and newlines first (no dependence on the copies), then the staged sequence bytes
-        const int np = s.np;
+        return;
+    }
+
+    // ================= consumers =================
+    const int ct = threadIdx.x - 32;
+    int       slot = 0;
+    unsigned  ph = 0;
+    for (;;) {
+        mbar_wait(&s.full[slot], ph);
+        const int np = s.np[slot];
+        if (np < 0) break;
+        const int64_t x0 = s.x0[slot], x1 = s.x1[slot];
         for (int k = 0; k < np; k++) {
-            const FePiece& pc = s.piece[k];
+            const FePiece& pc = s.piece[slot][k];
             const int64_t  O = pc.O;
             const int      h = pc.h;
             const int64_t  hp0 = O > x0 ? O : x0, hp1 = (O + h) < x1 ? (O + h) : x1;
             if (hp0 < hp1) {
                 const int64_t  gid = a.own_first + pc.read;
                 const uint64_t num = (uint64_t)(a.read_num_base + pc.frag + 1);
-                const int      fa = pc.fa, fb = pc.fa + pc.len;
+                const unsigned fa = (unsigned)pc.fa, fb = (unsigned)(pc.fa + pc.len);
                 const int64_t  nm0 = a.name_off[gid];
                 const int      nl = (int)(a.name_off[gid + 1] - nm0);
-                const int      dn = dec_digits64(num), da = dec_digits((uint32_t)fa), db = dec_digits((uint32_t)fb);
-                for (int64_t x = hp0 + threadIdx.x; x < hp1; x += FE_THREADS) {
+                const int      dn = dec_digits64(num), da = dec_digits(fa), db = dec_digits(fb);
+                for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
                     int     q = (int)(x - O);
                     uint8_t c;
                     if (q < 6) c = (uint8_t)(">read="[q]);
-                    else if ((q -= 6) < dn) c = dec_digit_at(num, dn, q);
+                    else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
                     else if ((q -= dn) < 1) c = ',';
                     else if ((q -= 1) < nl) c = a.names[nm0 + q];
                     else if ((q -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[q]);
-                    else if ((q -= 22) < da) c = dec_digit_at((uint64_t)fa, da, q);
+                    else if ((q -= 22) < da) c = dec_digit_at32(fa, da, q);
                     else if ((q -= da) < 1) c = '-';
-                    else if ((q -= 1) < db) c = dec_digit_at((uint64_t)fb, db, q);
+                    else if ((q -= 1) < db) c = dec_digit_at32(fb, db, q);
                     else c = '\n';
                     a.dst[x - a.w0] = c;
                 }
             }
             const int64_t s1 = O + h + pc.len;
-            if (threadIdx.x == 0 && s1 >= x0 && s1 < x1) a.dst[s1 - a.w0] = '\n';
-        }
-        mbar_wait(&s.bar, phase);
-        phase ^= 1;
-        for (int k = 0; k < np; k++) {
-            const FePiece& pc = s.piece[k];
+            if (ct == 0 && s1 >= x0 && s1 < x1) a.dst[s1 - a.w0] = '\n';
             if (pc.n > 0) {
                 uint8_t* d = a.dst + (pc.p0 - a.w0);
-                block_copy_from_smem(d, s.stage + pc.soff, pc.n_stage);
-                for (int q = pc.n_stage + threadIdx.x; q < pc.n; q += FE_THREADS) d[q] = pc.src[q]; // arena tail not covered by the bulk copy
+                consumers_copy_from_smem(d, s.stage[slot] + pc.soff, pc.n_stage, ct);
+                for (int q = pc.n_stage + ct; q < pc.n; q += FE_CONSUMERS) d[q] = pc.src[q]; // arena tail not covered by the bulk copy
             }
         }
-        if (!s.more) break;
-        __syncthreads(); // the stage and the piece list are rewritten by the next round
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&s.empty[slot]); // this warp no longer reads the slot
+        if (++slot == FE_SLOTS) { slot = 0; ph ^= 1; }
     }
 }
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
 {
     if (a.w1 <= a.w0 || a.G <= 0) return;
     int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
+    int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
     cudaFuncSetAttribute(k_fasta_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
-    k_fasta_emit<<<(unsigned)tiles, FE_THREADS, sizeof(FeSmem), st>>>(a);
+    k_fasta_emit<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);
 }
 
 // ================================================================ digest

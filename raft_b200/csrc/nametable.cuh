@@ -23,24 +23,30 @@ struct NameTable {
     unsigned long long seed;
 };
 
-// Incremental hash: bytes are consumed as little-endian 32-bit words (zero padded), one multiply
-// per word; the byte count is folded in at the end.
+// Incremental hash: bytes are consumed as little-endian 32-bit words (zero padded) by two independent
+// 32-bit multiplicative streams (3 integer instructions per word); the byte count is folded in at
+// the end and the 64 bits are finalised with mix64.  hash_name_smem in k1_paf.cu computes the same
+// value word-wise from shared memory.
+constexpr unsigned NH_K1 = 0x9E3779B1u, NH_K2 = 0x85EBCA77u;
+__device__ __forceinline__ unsigned long long name_hash_finish(unsigned a, unsigned b, unsigned n)
+{
+    unsigned long long r = mix64((((unsigned long long)a << 32) | b) ^ ((unsigned long long)n * 0x9E3779B97F4A7C15ull));
+    return r ? r : 1ull;
+}
 struct NameHasher {
-    unsigned long long h;
-    unsigned           w;
-    unsigned           n;
-    __device__ __forceinline__ void init(unsigned long long seed) { h = seed ^ 0x9E3779B97F4A7C15ull; w = 0; n = 0; }
+    unsigned a, b, w, n;
+    __device__ __forceinline__ void init(unsigned long long seed) { a = (unsigned)seed ^ 0x9E3779B9u; b = (unsigned)(seed >> 32) ^ 0x85EBCA6Bu; w = 0; n = 0; }
+    __device__ __forceinline__ void word(unsigned x) { a = (a ^ x) * NH_K1; b = b * NH_K2 + x; }
     __device__ __forceinline__ void add(unsigned c)
     {
         w |= c << ((n & 3u) * 8u);
         n++;
-        if ((n & 3u) == 0) { h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29; w = 0; }
+        if ((n & 3u) == 0) { word(w); w = 0; }
     }
     __device__ __forceinline__ unsigned long long finish()
     {
-        if (n & 3u) { h = (h ^ w) * 0xD6E8FEB86659FD93ull; h ^= h >> 29; }
-        unsigned long long r = mix64(h ^ ((unsigned long long)n << 32));
-        return r ? r : 1ull;
+        if (n & 3u) word(w);
+        return name_hash_finish(a, b, n);
     }
 };
 
