@@ -134,12 +134,13 @@ __device__ __forceinline__ int64_t lb_signed(uint64_t v)
 }
 
 // ------------------------------------------------------------------ decimal text
+static __device__ __constant__ unsigned c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+// decimal digits of v: bit length * log10(2) (1233/4096), corrected by one table compare
 __device__ __forceinline__ int dec_digits(uint32_t v)
 {
-    int d = 1;
-    d += v >= 10u; d += v >= 100u; d += v >= 1000u; d += v >= 10000u; d += v >= 100000u;
-    d += v >= 1000000u; d += v >= 10000000u; d += v >= 100000000u; d += v >= 1000000000u;
-    return d;
+    v |= 1u;
+    int t = ((32 - __clz(v)) * 1233) >> 12;
+    return t + (v >= c_pow10[t]);
 }
 __device__ __forceinline__ int dec_digits64(uint64_t v)
 {
@@ -163,6 +164,12 @@ __device__ __forceinline__ uint8_t* put_dec_back(uint8_t* end, uint32_t v)
         v = q;
     } while (v);
     return end;
+}
+// v has exactly nd decimal digits
+__device__ __forceinline__ uint8_t* put_u32_nd(uint8_t* p, uint32_t v, int nd)
+{
+    put_dec_back(p + nd, v);
+    return p + nd;
 }
 __device__ __forceinline__ uint8_t* put_i32(uint8_t* p, int32_t v)
 {

@@ -26,19 +26,67 @@ constexpr int CE_MAX_SLOT_BYTES = 40;               // "read 2147483647 " (16) +
 constexpr int CE_CAP = 16384;                       // shared-memory text buffer; tiles with more text (tiny reads) use the direct path
 constexpr int CE_SMEM = CE_CAP + 32;
 
-// text of one slot at p; returns the end.  bin < nb: "pos,cov " ; bin == nb (sentinel): "\n"; bin == 0 is preceded by "read i "
-__device__ __forceinline__ uint8_t* cov_slot_text(uint8_t* p, int64_t read_id, int64_t bin, bool sentinel, int reso, int cov)
-{
-    if (bin == 0) {
-        p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
-        uint64_t id = (uint64_t)read_id;
-        int      nd = dec_digits64(id);
-        for (int d = nd - 1; d >= 0; d--) { p[d] = (uint8_t)('0' + (unsigned)(id % 10ull)); id /= 10ull; }
-        p += nd; *p++ = ' ';
+// Per-thread walk over CE_PER consecutive slots.  A slot is one bin ("pos,cov ") or the read's sentinel ("\n");
+// the first slot of a read is preceded by "read i ".  The walk keeps (bin, slots left in the read) in 32-bit
+// registers and only touches slot_off when it crosses into the next read.
+struct SlotWalk {
+    const int64_t* __restrict__ slot_off;
+    int64_t r;     // current read (local index)
+    int64_t re;    // one past its last slot
+    int     bin;   // index of the current slot inside the read
+    int     left;  // slots left in the read including the current one (clamped)
+    __device__ __forceinline__ void init(const int64_t* so, int64_t read, int64_t g)
+    {
+        slot_off = so; r = read;
+        const int64_t rs = so[read];
+        re = so[read + 1];
+        bin = (int)(g - rs);
+        const int64_t rem = re - g;
+        left = rem > (1 << 30) ? (1 << 30) : (int)rem;
     }
-    if (sentinel) { *p++ = '\n'; return p; }
-    p = put_i32(p, (int32_t)(bin * reso)); *p++ = ',';
-    p = put_i32(p, cov); *p++ = ' ';
+    __device__ __forceinline__ void next()
+    {
+        bin++;
+        if (--left == 0) {
+            r++;
+            const int64_t nre = slot_off[r + 1];
+            const int64_t rem = nre - re;
+            left = rem > (1 << 30) ? (1 << 30) : (int)rem;
+            re = nre; bin = 0;
+        }
+    }
+};
+
+// digit counts of one slot packed as pos | cov << 4 | neg << 8 (cov may be negative only on invalid input)
+__device__ __forceinline__ int slot_digits(int bin, int reso, int cov)
+{
+    const unsigned ucov = cov < 0 ? (unsigned)(-(int64_t)cov) : (unsigned)cov;
+    return dec_digits((uint32_t)bin * (uint32_t)reso) | (dec_digits(ucov) << 4) | ((cov < 0) << 8);
+}
+
+// text of this thread's slots at p (shared or local memory after inlining); returns the end
+__device__ __forceinline__ uint8_t* cov_format_slots(uint8_t* p, SlotWalk w, int nmine, const int* cv, const int* dg, int reso, int64_t own_first)
+{
+#pragma unroll
+    for (int k = 0; k < CE_PER; k++) {
+        if (k < nmine) {
+            if (w.bin == 0) {
+                p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
+                uint64_t id = (uint64_t)(own_first + w.r);
+                int      nd = dec_digits64(id);
+                for (int d = nd - 1; d >= 0; d--) { p[d] = (uint8_t)('0' + (unsigned)(id % 10ull)); id /= 10ull; }
+                p += nd; *p++ = ' ';
+            }
+            if (w.left == 1) {
+                *p++ = '\n';
+            } else {
+                p = put_u32_nd(p, (uint32_t)w.bin * (uint32_t)reso, dg[k] & 15); *p++ = ',';
+                if (dg[k] >> 8) *p++ = '-';
+                p = put_u32_nd(p, cv[k] < 0 ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], (dg[k] >> 4) & 15); *p++ = ' ';
+            }
+            w.next();
+        }
+    }
     return p;
 }
 
@@ -49,33 +97,33 @@ __global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitAr
     __shared__ int ws[34];
     const int64_t  tile = a.tile_first + blockIdx.x;
     const int64_t  g0 = tile * COV_TILE_SLOTS + (int64_t)threadIdx.x * CE_PER;
+    const int      nmine = g0 >= a.n_slots ? 0 : (a.n_slots - g0 < CE_PER ? (int)(a.n_slots - g0) : CE_PER);
     int            mine = 0;
-    int64_t        ri = 0, rs = 0, re = 0; // current read, its first slot, one past its last slot
-    int            cv[CE_PER];
-    if (g0 < a.n_slots) {
+    int            cv[CE_PER], dg[CE_PER];
+    SlotWalk       w0;
+    if (nmine) {
         // the tile map bounds the search to the reads that intersect this tile
         int64_t lo = a.tile_read[tile], hi = (int64_t)a.tile_read[tile + 1] + 1;
         while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a.slot_off[mid] <= g0) lo = mid; else hi = mid; }
-        ri = lo; rs = a.slot_off[ri]; re = a.slot_off[ri + 1];
+        w0.init(a.slot_off, lo, g0);
     }
-    if (g0 + CE_PER <= a.n_slots) { // 4 consecutive ints, 16-byte aligned
+    if (nmine == CE_PER) { // 4 consecutive ints, 16-byte aligned
         int4 v = *reinterpret_cast<const int4*>(a.cov + g0);
         cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < CE_PER; k++) cv[k] = (g0 + k < a.n_slots) ? a.cov[g0 + k] : 0;
+        for (int k = 0; k < CE_PER; k++) cv[k] = (k < nmine) ? a.cov[g0 + k] : 0;
     }
     {
-        int64_t r_ = ri, rs_ = rs, re_ = re;
+        SlotWalk w = w0;
 #pragma unroll
         for (int k = 0; k < CE_PER; k++) {
-            int64_t g = g0 + k;
-            if (g < a.n_slots) {
-                while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
-                int64_t bin = g - rs_;
-                if (bin == 0) mine += 5 + dec_digits64((uint64_t)(a.own_first + r_)) + 1;
-                if (g == re_ - 1) mine += 1;
-                else mine += dec_digits((uint32_t)(bin * a.reso)) + 1 + dec_len_i32(cv[k]) + 1;
+            dg[k] = 0;
+            if (k < nmine) {
+                if (w.bin == 0) mine += 5 + dec_digits64((uint64_t)(a.own_first + w.r)) + 1;
+                if (w.left == 1) mine += 1;
+                else { dg[k] = slot_digits(w.bin, a.reso, cv[k]); mine += (dg[k] & 15) + ((dg[k] >> 4) & 15) + (dg[k] >> 8) + 2; }
+                w.next();
             }
         }
     }
@@ -88,36 +136,16 @@ __global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitAr
     const int64_t o0 = a.tile_off[tile], o1 = o0 + tot;
     const int64_t c0 = o0 > a.w0 ? o0 : a.w0, c1 = o1 < a.w1 ? o1 : a.w1;
     if (c0 >= c1) return;
-    if (tot > a.text_cap) {
-        // direct path (rare: thousands of tiny reads in one tile): format privately, store byte-wise with clipping
-        uint8_t  loc[CE_PER * CE_MAX_SLOT_BYTES];
-        uint8_t* p = loc;
-        int64_t  r_ = ri, rs_ = rs, re_ = re;
-        for (int k = 0; k < CE_PER; k++) {
-            int64_t g = g0 + k;
-            if (g < a.n_slots) {
-                while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
-                p = cov_slot_text(p, a.own_first + r_, g - rs_, g == re_ - 1, a.reso, cv[k]);
-            }
-        }
-        int64_t x = o0 + ex;
-        for (uint8_t* q = loc; q < p; q++, x++) if (x >= a.w0 && x < a.w1) a.dst[x - a.w0] = *q;
-        return;
-    }
     const uintptr_t gdst0 = (uintptr_t)a.dst + (uintptr_t)(o0 - a.w0); // address of stream byte o0 (may precede dst)
     const int       phase = (int)(gdst0 & 15);
-    {
-        uint8_t* p = sbuf + phase + ex;
-        int64_t  r_ = ri, rs_ = rs, re_ = re;
-#pragma unroll
-        for (int k = 0; k < CE_PER; k++) {
-            int64_t g = g0 + k;
-            if (g < a.n_slots) {
-                while (g >= re_) { r_++; rs_ = re_; re_ = a.slot_off[r_ + 1]; }
-                p = cov_slot_text(p, a.own_first + r_, g - rs_, g == re_ - 1, a.reso, cv[k]);
-            }
-        }
+    if (tot > a.text_cap) { // rare (thousands of tiny reads in one tile): format privately, store byte-wise with clipping
+        uint8_t  loc[CE_PER * CE_MAX_SLOT_BYTES];
+        uint8_t* e = cov_format_slots(loc, w0, nmine, cv, dg, a.reso, a.own_first);
+        int64_t  x = o0 + ex;
+        for (uint8_t* q = loc; q < e; q++, x++) if (x >= a.w0 && x < a.w1) a.dst[x - a.w0] = *q;
+        return;
     }
+    cov_format_slots(sbuf + phase + ex, w0, nmine, cv, dg, a.reso, a.own_first);
     __syncthreads();
     // store [c0, c1): head bytes, aligned 128-bit body, tail bytes
     const uintptr_t ga0 = gdst0 + (uintptr_t)(c0 - o0), ga1 = gdst0 + (uintptr_t)(c1 - o0);
