@@ -95,6 +95,7 @@ class Context:
         if self._h:
             self.L.raftgpu_destroy(self._h)
             self._h = C.c_void_p()
+        self._keep = []  # borrowed inputs may be released now
 
     def __enter__(self):
         return self
