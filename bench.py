@@ -202,6 +202,8 @@ def ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries the JSON line only
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from raft_b200 import sharded

@@ -404,6 +404,7 @@ extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int6
     CK(cudaSetDevice(ctx->device));
     int st = raftgpu_reset(ctx);
     if (st) return st;
+    cudaEventRecord(ctx->ev[0], ctx->st);
     int64_t name_bytes = 0, seq_bytes = 0;
     CK(cudaMemcpy(&name_bytes, name_off + n, 8, cudaMemcpyDefault));
     ctx->n = n; ctx->m = own_count; ctx->own_first = own_first;
@@ -430,7 +431,10 @@ extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int6
     else ctx->d_seq = nullptr;
     std::string first;
     if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
-    return build_layout_and_names(ctx, first);
+    st = build_layout_and_names(ctx, first);
+    cudaEventRecord(ctx->ev[1], ctx->st);
+    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_set_reads, ctx->ev[0], ctx->ev[1]);
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------ PAF
