@@ -53,6 +53,7 @@ struct Misc {
     int                work_counter;
     int                pad;
     ErrState           err;
+    ErrState           err_range;
     long long          n_records_out;
     unsigned long long stats[2];
     unsigned long long digest;
@@ -88,6 +89,8 @@ struct raftgpu_ctx {
     DevBuf  b_text;
     std::vector<uint8_t> carry;
     bool    first_is_local = true, rec0_external = false, sym_external = false, paf_done = false;
+    bool    q_scattered = false; // query sides went into the difference array during tokenisation
+    int     h_sym = 0;           // host copy of the (local) symmetric flag after the last ingest
     int64_t paf_bytes = 0;
 
     DevBuf  b_misc, b_status;
@@ -227,12 +230,13 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     if (ctx->st_h2d) CK(cudaStreamSynchronize(ctx->st_h2d)); // an upload in flight still reads the caller's host arena
     ctx->seq_host = nullptr; ctx->seq_host_bytes = 0; ctx->seq_upload_started = false; ctx->n_chunks = 0;
     Misc h{};
-    h.err.index = LLONG_MAX;
+    h.err.index = LLONG_MAX; h.err_range.index = LLONG_MAX;
     CK(cudaMemcpyAsync(ctx->b_misc.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->have_reads = ctx->have_seq = false; ctx->n = ctx->m = ctx->own_first = 0;
     ctx->n_rec = 0; ctx->carry.clear(); ctx->first_is_local = true; ctx->rec0_external = ctx->sym_external = false;
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
+    ctx->q_scattered = false; ctx->h_sym = 0;
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
     ctx->emit_pending = false;
@@ -244,9 +248,10 @@ int raftgpu_reset(raftgpu_ctx* ctx)
 // ------------------------------------------------------------------------------------------------
 static int fetch_err(raftgpu_ctx* ctx)
 { // read the device error word (stream must be synchronised by the caller or here)
-    ErrState e;
-    CK(cudaMemcpyAsync(&e, &ctx->misc()->err, sizeof e, cudaMemcpyDeviceToHost, ctx->st));
+    ErrState e2[2];
+    CK(cudaMemcpyAsync(e2, &ctx->misc()->err, sizeof e2, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    ErrState e = e2[0].index != LLONG_MAX ? e2[0] : e2[1]; // unknown names / duplicates first, then range errors of the fused scatter
     if (e.index != LLONG_MAX) {
         ctx->err_index = e.index;
         char buf[160];
@@ -334,6 +339,14 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
     CKL();
     int64_t tot[3], seq_total = 0;
     CK(cudaMemcpyAsync(&tot[0], ctx->b_slot_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    {   // first read of every 1024-slot tile of coverage.txt (used by the fused sizing in the scan and by the emitter)
+        const int T = cov_tiles(tot[0]);
+        CK(ctx->b_cov_tile_read.ensure(sizeof(int32_t) * (size_t)(T + 2)));
+        CK(ctx->b_cov_tile_bytes.ensure(sizeof(int32_t) * (size_t)(T + 1)));
+        launch_cov_tile_index(ctx->b_slot_off.as<int64_t>(), m, tot[0], ctx->b_cov_tile_read.as<int32_t>(), ctx->st);
+        CKL();
+    }
     CK(cudaMemcpyAsync(&tot[1], ctx->b_rep_cap_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&tot[2], ctx->b_cut_cap_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&seq_total, ctx->d_seq_off + m, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -451,6 +464,8 @@ static int ensure_records(raftgpu_ctx* ctx, int64_t cap)
     return RAFTGPU_OK;
 }
 
+static int zero_diff(raftgpu_ctx* ctx);
+
 // tokenise `len` bytes of device text (complete lines, except that the last line may lack its newline)
 static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
 {
@@ -466,6 +481,8 @@ static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
     CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(tiles + 8)));
     int st = ensure_records(ctx, ctx->n_rec + len / 48 + 1024);
     if (st) return st;
+    if ((st = zero_diff(ctx))) return st; // the tokenizer adds the query sides as it decodes them
+    ctx->q_scattered = true;
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(cudaMemsetAsync(ctx->b_status.p, 0, sizeof(uint64_t) * (size_t)tiles, ctx->st));
         CK(cudaMemsetAsync(&M->ticket, 0, sizeof(int), ctx->st));
@@ -476,10 +493,14 @@ static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
         a.rec0 = M->rec0; a.first_is_local = ctx->first_is_local ? 1 : 0; a.n_tiles = tiles;
         a.status = ctx->b_status.as<uint64_t>(); a.ticket = &M->ticket; a.sym_flag = &M->sym_flag; a.err = &M->err;
         a.n_records_out = (int64_t*)&M->n_records_out; a.names = ctx->nt;
+        // a retry (record capacity overflow) decodes the same lines again: their query sides are already in
+        a.diff = attempt == 0 ? ctx->b_cov.as<int32_t>() : nullptr; a.slot_off = ctx->b_slot_off.as<int64_t>(); a.reso = ctx->prm.reso;
+        a.own_first = ctx->own_first; a.own_count = ctx->m; a.err_range = &M->err_range;
         CK(launch_paf_tokenize(a, ctx->st));
         ctx->launches++;
         long long n_out = 0;
         CK(cudaMemcpyAsync(&n_out, &M->n_records_out, sizeof n_out, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&ctx->h_sym, &M->sym_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
         if ((st = fetch_err(ctx))) return st;
         if (n_out > 0x7fffffffll) FAIL(RAFTGPU_E_ARG, "more than 2^31-1 PAF records (the reference counts them in an int, chop.hpp:139)");
         if (n_out <= ctx->rec_cap) { ctx->n_rec = n_out; return RAFTGPU_OK; }
@@ -590,7 +611,7 @@ extern "C" int raftgpu_set_symmetric(raftgpu_ctx* ctx, int32_t flag)
     CK(cudaSetDevice(ctx->device));
     int f = flag != 0;
     CK(cudaMemcpy(&ctx->misc()->sym_flag, &f, sizeof(int), cudaMemcpyHostToDevice));
-    ctx->sym_external = true;
+    ctx->sym_external = true; ctx->h_sym = f;
     return RAFTGPU_OK;
 }
 
@@ -618,7 +639,12 @@ static int accumulate_local(raftgpu_ctx* ctx)
 {
     int st = zero_diff(ctx);
     if (st) return st;
-    launch_scatter_records(scatter_args(ctx), ctx->st);
+    ScatterArgs a = scatter_args(ctx);
+    a.skip_query = ctx->q_scattered ? 1 : 0;
+    // symmetric overlaps + query sides already in: nothing left to add (target sides do not contribute, repeat.hpp:54)
+    const bool sym_known = ctx->sym_external || ctx->paf_done;
+    if (a.skip_query && sym_known && ctx->h_sym) return RAFTGPU_OK;
+    launch_scatter_records(a, ctx->st);
     CKL();
     return RAFTGPU_OK;
 }
@@ -700,7 +726,8 @@ extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
     // K2b: coverage = inclusive scan of the difference array
     cudaEventRecord(ctx->ev[3], ctx->st);
     CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_cov(ctx->n_slots) + scan_tiles_small(std::max<int64_t>(m, ctx->cut_cap_total + m)) + 16)));
-    launch_scan_cov_inplace(ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CovSizeArgs cs{ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_slot_off.as<int64_t>(), ctx->b_cov_tile_read.as<int32_t>(), ctx->own_first, P.reso};
+    launch_scan_cov_inplace(ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, cs, ctx->st);
     CKL();
     cudaEventRecord(ctx->ev[4], ctx->st);
     // K3: repeats + cut points
@@ -790,16 +817,8 @@ static int layout_outputs(raftgpu_ctx* ctx)
     CKL();
     // coverage.txt tiles
     const int T = cov_tiles(ctx->n_slots);
-    CK(ctx->b_cov_tile_bytes.ensure(sizeof(int32_t) * (size_t)(T + 1))); CK(ctx->b_cov_tile_off.ensure(sizeof(int64_t) * (size_t)(T + 1)));
-    CK(ctx->b_cov_tile_read.ensure(sizeof(int32_t) * (size_t)(T + 2)));
-    launch_cov_tile_index(ctx->b_slot_off.as<int64_t>(), m, ctx->n_slots, ctx->b_cov_tile_read.as<int32_t>(), ctx->st);
-    CKL();
-    CovEmitArgs ca{};
-    ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
-    ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_bytes = ctx->b_cov_tile_bytes.as<int32_t>(); ca.tile_first = 0;
-    ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
-    launch_cov_sizes(ca, ctx->st);
-    CKL();
+    CK(ctx->b_cov_tile_off.ensure(sizeof(int64_t) * (size_t)(T + 1)));
+    // tile byte counts were produced by the coverage scan (fused sizing)
     launch_scan_i32_to_i64(ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_off.as<int64_t>(), T, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
     CKL();
     ctx->h_cov_tile_off.resize(T + 1); ctx->h_rep_line_off.resize(m + 1);

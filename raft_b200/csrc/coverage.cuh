@@ -1,0 +1,30 @@
+// coverage.cuh — interval -> difference-array update shared by the tokenizer (query sides, fused) and K2.
+#pragma once
+#include "kernels.h"
+
+namespace raftk {
+
+__device__ __forceinline__ void err_min(ErrState* err, int code, long long index)
+{
+    long long old = atomicMin(&err->index, index);
+    if (index <= old) err->code = code;
+}
+
+// Adds interval [s,e) of owned local read lr: +1 at its first bin, -1 one past its last bin (repeat.hpp:62-77:
+// lo = max(s,0)/reso, bins lo..(e-1)/reso when e-1 >= lo*reso).  Returns false when it would leave the read's bins
+// (the reference writes out of bounds there).
+__device__ __forceinline__ bool add_interval(int32_t* diff, const int64_t* __restrict__ slot_off, int64_t lr, int s, int e, int reso)
+{
+    int64_t base = slot_off[lr];
+    int64_t nb = slot_off[lr + 1] - base - 1;
+    int64_t lo = (int64_t)(s < 0 ? 0 : s) / reso;
+    int64_t em = (int64_t)e - 1;
+    if (em < lo * reso) return true; // nothing covered (repeat.hpp:69 never true)
+    int64_t hi = em / reso;
+    if (hi >= nb) return false;
+    atomicAdd(diff + base + lo, 1);
+    atomicAdd(diff + base + hi + 1, -1);
+    return true;
+}
+
+} // namespace raftk

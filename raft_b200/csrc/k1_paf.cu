@@ -21,7 +21,7 @@
 //  * a trailing '\r' (kseq.h:189-190) can only sit in the last field of a line, which is never
 //    one of the used fields of a valid record, so it needs no handling;
 //  * symmetric flag: some record k >= 1 mirrors record 0 (chop.hpp:171-184).
-#include "kernels.h"
+#include "coverage.cuh"
 #include "nametable.cuh"
 
 namespace raftk {
@@ -342,6 +342,10 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
         if (rec < a.rec_cap) {
             a.qid[rec] = pr.qid; a.tid[rec] = pr.tid; a.qs[rec] = pr.qs; a.qe[rec] = pr.qe;
             a.ts[rec] = pr.ts; a.te[rec] = pr.te; a.strand[rec] = (uint8_t)pr.strand;
+        }
+        if (a.diff) { // fused K2a: the query side of every record covers [qs, qe) of its read (repeat.hpp:50-53)
+            const int64_t lq = (int64_t)pr.qid - a.own_first;
+            if (lq >= 0 && lq < a.own_count && !add_interval(a.diff, a.slot_off, lq, pr.qs, pr.qe, a.reso)) err_min(a.err_range, RAFTK_E_RANGE, rec);
         }
         // chop.hpp:171-184: record k >= 1 mirrors record 0
         if (r0[6] && (rec != 0 || !a.first_is_local) && r0[0] == pr.tid && r0[1] == pr.qid && r0[2] == pr.ts &&

@@ -10,7 +10,8 @@
 // Which intervals contribute (repeat.hpp:48-58, chop.hpp:165-169): the query side of every record;
 // the target side too when overlaps are not symmetric and target != query.
 // Bin range of [s, e) (repeat.hpp:62-77): lo = max(s,0)/reso, bins lo..(e-1)/reso when e-1 >= lo*reso.
-#include "kernels.h"
+#include "coverage.cuh"
+#include "covtext.cuh"
 
 namespace raftk {
 
@@ -86,7 +87,9 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ROUNDS = 4;
 constexpr int CS_TILE = CS_THREADS * 4 * CS_ROUNDS; // 4096 ints = 16 KiB
 
-__global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ data, int64_t n, uint64_t* status, int* ticket)
+// The scan is memory-bound with most issue slots idle, so it also sizes coverage.txt: every thread knows the final
+// coverage of its 16 slots and adds their text bytes into the 1024-slot tile counters the emitter (K5a) uses.
+__global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ data, int64_t n, uint64_t* status, int* ticket, CovSizeArgs cs)
 {
     __shared__ int      ws[34];
     __shared__ uint64_t bcast;
@@ -123,12 +126,17 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
     int warp_ex = __shfl_sync(FULL, bex, 31) - 0; // lane 31's exclusive prefix == sum of earlier warps
     uint64_t pre = lookback_block(status, tile, (uint64_t)(int64_t)btot, &bcast);
     int      p0 = (int)lb_signed(pre) + warp_ex;
+    int      text_bytes = 0;
 #pragma unroll
     for (int r = 0; r < CS_ROUNDS; r++) {
         int64_t i = tbase + r * 128 + lane * 4;
         int     a = p0 + lane_ex[r];
         int4    o;
         o.x = a + v[r].x; o.y = o.x + v[r].y; o.z = o.y + v[r].z; o.w = o.z + v[r].w;
+        if (cs.tile_bytes && i < n) {
+            const int cvv[4] = {o.x, o.y, o.z, o.w};
+            text_bytes += cov_text_size4(cs.slot_off, cs.tile_read, i, (n - i) < 4 ? (int)(n - i) : 4, cvv, cs.reso, cs.own_first);
+        }
         if (full) {
             *reinterpret_cast<int4*>(data + i) = o;
         } else {
@@ -136,39 +144,23 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
             if (i + 2 < n) data[i + 2] = o.z; if (i + 3 < n) data[i + 3] = o.w;
         }
     }
+    if (cs.tile_bytes) { // a warp's 512 slots lie inside one 1024-slot text tile
+        text_bytes = warp_sum(text_bytes);
+        if (lane == 0 && text_bytes) atomicAdd(cs.tile_bytes + tbase / COV_TILE_SLOTS, text_bytes);
+    }
 }
 int  scan_tiles_cov(int64_t n) { return (int)((n + CS_TILE - 1) / CS_TILE); }
-void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, cudaStream_t st)
+void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st)
 {
     int tiles = scan_tiles_cov(n);
     if (tiles == 0) return;
     cudaMemsetAsync(status, 0, sizeof(uint64_t) * tiles, st);
     cudaMemsetAsync(ticket, 0, sizeof(int), st);
-    k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(data, n, status, ticket);
+    if (cs.tile_bytes) cudaMemsetAsync(cs.tile_bytes, 0, sizeof(int32_t) * (size_t)((n + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS), st);
+    k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(data, n, status, ticket, cs);
 }
 
 // ---------------------------------------------------------------- scatter
-__device__ __forceinline__ void err_min(ErrState* err, int code, long long index)
-{
-    long long old = atomicMin(&err->index, index);
-    if (index <= old) err->code = code;
-}
-
-// adds interval [s,e) of owned local read lr; returns false when it would leave the read's bins
-__device__ __forceinline__ bool add_interval(int32_t* diff, const int64_t* __restrict__ slot_off, int64_t lr, int s, int e, int reso)
-{
-    int64_t base = slot_off[lr];
-    int64_t nb = slot_off[lr + 1] - base - 1;
-    int64_t lo = (int64_t)(s < 0 ? 0 : s) / reso;
-    int64_t em = (int64_t)e - 1;
-    if (em < lo * reso) return true; // nothing covered (repeat.hpp:69 never true)
-    int64_t hi = em / reso;
-    if (hi >= nb) return false;
-    atomicAdd(diff + base + lo, 1);
-    atomicAdd(diff + base + hi + 1, -1);
-    return true;
-}
-
 __global__ void __launch_bounds__(256) k_scatter_records(ScatterArgs a)
 {
     const bool    sym = *a.sym_flag != 0;
@@ -176,7 +168,7 @@ __global__ void __launch_bounds__(256) k_scatter_records(ScatterArgs a)
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.n_rec; k += stride) {
         int     q = a.qid[k], t = a.tid[k];
         int64_t lq = (int64_t)q - a.own_first;
-        if (lq >= 0 && lq < a.own_count)
+        if (!a.skip_query && lq >= 0 && lq < a.own_count)
             if (!add_interval(a.diff, a.slot_off, lq, a.qs[k], a.qe[k], a.reso)) err_min(a.err, RAFTK_E_RANGE, k);
         if (!sym && t != q) {
             int64_t lt = (int64_t)t - a.own_first;

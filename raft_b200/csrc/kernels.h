@@ -37,6 +37,12 @@ struct PafTokArgs {
     ErrState*      err;
     int64_t*       n_records_out;
     NameTable      names;
+    // fused K2a: query-side intervals (they contribute whatever the symmetric flag turns out to be, repeat.hpp:50-53)
+    int32_t*       diff;      // null: do not scatter
+    const int64_t* slot_off;
+    int            reso;
+    int64_t        own_first, own_count;
+    ErrState*      err_range; // separate from `err`: an unknown name outranks a range error, as in the oracle
 };
 
 int         paf_tokenize_tiles(int64_t nbytes);
@@ -50,9 +56,17 @@ void launch_read_layout(const int64_t* seq_off_local, int64_t m, int reso, int p
 // exclusive scan int32[n] -> int64[n+1]; tmp_status must hold scan_tiles(n) uint64 (+1 int ticket after it), zeroed by the launcher
 int  scan_tiles_small(int64_t n);
 void launch_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, uint64_t* status, int* ticket, cudaStream_t st);
-// in-place inclusive scan of the int32 difference array
+// in-place inclusive scan of the int32 difference array, fused with the sizing of coverage.txt (bytes per 1024-slot tile)
+constexpr int COV_TILE_SLOTS = 1024;
+struct CovSizeArgs {
+    int32_t*       tile_bytes; // null: scan only
+    const int64_t* slot_off;
+    const int32_t* tile_read;
+    int64_t        own_first;
+    int            reso;
+};
 int  scan_tiles_cov(int64_t n);
-void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, cudaStream_t st);
+void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st);
 
 struct ScatterArgs {
     const int32_t *qid, *tid, *qs, *qe, *ts, *te;
@@ -63,6 +77,7 @@ struct ScatterArgs {
     int64_t        own_first, own_count;
     const int*     sym_flag;
     ErrState*      err;
+    int            skip_query; // query sides were already added by the tokenizer
 };
 void launch_scatter_records(const ScatterArgs& a, cudaStream_t st);
 // routed endpoints: int32 triples (global read id, start, end)
@@ -114,7 +129,6 @@ void launch_rep_compact(const int32_t* rep_cnt, const int64_t* rep_cap_off, cons
                         cudaStream_t st);
 
 // ---------------------------------------------------------------- K5 (k5_emit.cu)
-constexpr int COV_TILE_SLOTS = 1024;
 struct CovEmitArgs {
     const int32_t* cov;      // scanned slots
     const int64_t* slot_off; // m+1
