@@ -8,7 +8,7 @@
 // paf.hpp:84) by popcounts, the tile's record count by a block scan, its first record index by a
 // decoupled look-back over tiles, the j-th valid line by select on the mask, and the nine field
 // boundaries by ffs hops over the tab mask.  Fields are decoded straight from shared memory:
-// names are hashed four bytes per step (funnel-shifted unaligned words), numbers by a digit loop.
+// names are hashed four bytes per step (funnel-shifted unaligned words), numbers eight digits at a time (SWAR).
 // Lines that run past the staged bytes (e.g. kilobyte cg:Z: CIGAR tags) take a byte-wise path
 // that reads global memory.
 //
@@ -26,7 +26,9 @@
 
 namespace raftk {
 
-constexpr int K1_THREADS = 256;
+constexpr int K1_THREADS = 160;             // 5 warps: one decode round covers the ~135 records of a typical tile
+constexpr int K1_WPT = 4;                   // mask words per thread when enumerating line starts (160 * 4 >= 513)
+constexpr int K1_LCAP = 1024;               // line list capacity of the dense validity pass (more lines: in-thread pass)
 constexpr int K1_TILE = 16384;             // bytes of text whose newlines a CTA owns
 constexpr int K1_OVER = 1024;              // staged overhang: lines starting near the tile end
 constexpr int K1_STAGE = K1_TILE + K1_OVER;
@@ -36,10 +38,13 @@ constexpr int K1_TWORDS = K1_TILE / 32;    // 512: line starts live in bits [0, 
 constexpr int K1_MAXREC = K1_TILE / 10 + 2; // a record has >= 9 tabs + newline: at most 1639 start in a tile
 
 struct __align__(16) K1Smem {
+    uint8_t  pad_front[16];       // lets the 8-byte number window start before the tile
     uint8_t  text[K1_STAGE + 16];
     unsigned nl[K1_WORDS + 1];    // byte is '\n'   (+1: all-ones sentinel word)
     unsigned tab[K1_WORDS + 1];   // byte is '\t'   (+1: all-ones sentinel word)
     uint16_t vpos[K1_MAXREC];     // start of the j-th record of the tile, tile relative
+    uint16_t lpos[K1_LCAP];       // start of the j-th non-empty line (bit 15: it is a record)
+    int      n_invalid;
     uint64_t bar;
     uint64_t bcast;
     int      scan_ws[34];
@@ -187,14 +192,37 @@ __device__ __noinline__ int parse_num_generic(const uint8_t* s, int a, int b)
     for (int i = a; i < b; i++) { num.add(s[i]); if (num.st == 3) break; }
     return num.value();
 }
-// fast path: 1..9 plain digits filling the whole field
-__device__ __forceinline__ int parse_num_smem(const uint8_t* s, int a, int b)
+// four ASCII digits (first digit in the lowest byte) -> value
+__device__ __forceinline__ unsigned parse4(unsigned w)
 {
-    unsigned acc = 0;
-    int      i = a;
-    for (; i < b; i++) { unsigned d = (unsigned)s[i] - '0'; if (d > 9u) break; acc = acc * 10u + d; }
-    if (i == b && b > a && b - a <= 9) return (int)acc;
-    return parse_num_generic(s, a, b);
+    unsigned d = w & 0x0F0F0F0Fu;
+    d = d * 10u + (d >> 8);                 // byte0 = 10*d0 + d1, byte2 = 10*d2 + d3
+    return (d & 0xFFu) * 100u + ((d >> 16) & 0xFFu);
+}
+// Field [a, b) of 1..8 plain digits: take the 8 bytes ending at b, turn the bytes before the field into '0',
+// check that all are digits and convert both halves at once.  Anything else (sign, spaces, junk, 9+ digits)
+// goes to the strtol-exact byte loop.  `tw` = 32-bit view of the staged text INCLUDING the 16-byte front pad.
+__device__ __forceinline__ int parse_num_smem(const uint8_t* text, const unsigned* tw, int a, int b)
+{
+    const int n = b - a;
+    if (n < 1 || n > 8) return parse_num_generic(text, a, b);
+    const int      k = b - 8 + 16; // >= 8 thanks to the front pad
+    const int      idx = k >> 2;
+    const unsigned sh = (unsigned)(k & 3) * 8u;
+    const unsigned x0 = tw[idx], x1 = tw[idx + 1], x2 = tw[idx + 2];
+    unsigned       w0 = __funnelshift_r(x0, x1, sh), w1 = __funnelshift_r(x1, x2, sh);
+    const int      lead = 8 - n;
+    if (lead >= 4) {
+        const unsigned m = 0xFFFFFFFFu << (8 * (lead - 4));
+        w0 = 0x30303030u; w1 = (w1 & m) | (0x30303030u & ~m);
+    } else {
+        const unsigned m = 0xFFFFFFFFu << (8 * lead);
+        w0 = (w0 & m) | (0x30303030u & ~m);
+    }
+    const unsigned bad = ((w0 & 0xF0F0F0F0u) ^ 0x30303030u) | (((w0 + 0x06060606u) & 0xF0F0F0F0u) ^ 0x30303030u) |
+                         ((w1 & 0xF0F0F0F0u) ^ 0x30303030u) | (((w1 + 0x06060606u) & 0xF0F0F0F0u) ^ 0x30303030u);
+    if (bad) return parse_num_generic(text, a, b);
+    return (int)(parse4(w0) * 10000u + parse4(w1));
 }
 
 // hash of staged bytes [a, b): same value as NameHasher fed byte by byte
@@ -220,7 +248,7 @@ __device__ __forceinline__ unsigned long long hash_name_smem(const unsigned* sw,
     return name_hash_finish(hs.a, hs.b, (unsigned)n);
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
+__global__ void __launch_bounds__(K1_THREADS, 8) k_paf_tokenize(PafTokArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
@@ -248,53 +276,92 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
 
     // ---- newline / tab masks: one 16-byte group per lane, two lanes make one 32-bit word
     const uint4* t16 = reinterpret_cast<const uint4*>(s.text);
-    for (int g = tid; g < K1_STAGE / 16; g += K1_THREADS) { // 1088 groups; the last round is two full warps
+    for (int g = tid; g < K1_STAGE / 16; g += K1_THREADS) { // 1088 groups = 6 rounds of 160 + four full warps
         uint4    v = t16[g];
         unsigned mn = eq_mask16(v, 0x0A0A0A0Au), mt = eq_mask16(v, 0x09090909u);
         unsigned pn = __shfl_down_sync(FULL, mn, 1), pt = __shfl_down_sync(FULL, mt, 1);
         if (!(lane & 1)) { s.nl[g >> 1] = mn | (pn << 16); s.tab[g >> 1] = mt | (pt << 16); }
     }
-    if (tid == 0) { s.nl[K1_WORDS] = 0xFFFFFFFFu; s.tab[K1_WORDS] = 0xFFFFFFFFu; }
+    if (tid == 0) { s.nl[K1_WORDS] = 0xFFFFFFFFu; s.tab[K1_WORDS] = 0xFFFFFFFFu; s.n_invalid = 0; }
     __syncthreads();
 
     TextReader rd;
     rd.text = a.text; rd.nbytes = a.nbytes; rd.stage_lo = 0; rd.stage_len = 0; rd.swords = nullptr; rd.word = 0;
 
-    // ---- phase A: thread t owns mask words 2t, 2t+1 (thread 255 also word 512).  A byte p starts a non-empty line
-    // owned by this tile iff byte p-1 is '\n' inside the tile and byte p is not; the line is a record iff it has
-    // >= 9 tabs before its newline (paf.hpp:84).
-    const int wlo = tid * 2, whi = (tid == K1_THREADS - 1) ? K1_TWORDS + 1 : wlo + 2;
-    unsigned  vmask[3] = {0, 0, 0};
-    int       my_valid = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int w = wlo + i;
-        if (w >= whi) break;
-        unsigned prev = w ? (s.nl[w - 1] >> 31) : ((tile == 0) ? 1u : 0u); // the file's first byte starts a line
-        unsigned m = ((s.nl[w] << 1) | prev) & ~s.nl[w];
-        if (w == K1_TWORDS) m &= 1u;
-        unsigned v = 0;
-        while (m) {
-            int bit = __ffs(m) - 1; m &= m - 1;
-            int p = (w << 5) + bit;
-            int e = next_bit(s.nl, p);                 // the line's newline (>= K1_STAGE when it is not staged)
-            if (e > K1_STAGE) e = K1_STAGE;
-            int tabs = count_bits(s.tab, p, e);
-            if (tabs < 9 && e == K1_STAGE && t0 + K1_STAGE < a.nbytes) { // runs past the staged bytes: read on
-                rd.seek(t0 + K1_STAGE);
-                for (;;) { int c = rd.next(); if (c < 0 || c == '\n') break; if (c == '\t' && ++tabs >= 9) break; }
-            }
-            if (tabs >= 9) v |= 1u << bit;
+    // a line starting at tile-relative byte p is a record iff it has >= 9 tabs before its newline (paf.hpp:84)
+    auto is_record = [&](int p) -> bool {
+        int e = next_bit(s.nl, p);                 // the line's newline (>= K1_STAGE when it is not staged)
+        if (e > K1_STAGE) e = K1_STAGE;
+        int tabs = count_bits(s.tab, p, e);
+        if (tabs < 9 && e == K1_STAGE && t0 + K1_STAGE < a.nbytes) { // runs past the staged bytes: read on
+            rd.seek(t0 + K1_STAGE);
+            for (;;) { int c = rd.next(); if (c < 0 || c == '\n') break; if (c == '\t' && ++tabs >= 9) break; }
         }
-        vmask[i] = v;
-        my_valid += __popc(v);
-    }
-    int n_valid;
-    int ex = block_exclusive_sum<int, K1_THREADS>(my_valid, s.scan_ws, &n_valid);
+        return tabs >= 9;
+    };
+
+    // ---- phase A1: line starts.  Thread t owns mask words [4t, 4t+4).  Byte p starts a non-empty line owned by this
+    // tile iff byte p-1 is '\n' inside the tile (or p is the file's first byte) and byte p is not '\n'.
+    unsigned lsm[K1_WPT];
+    int      my_lines = 0;
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        unsigned v = vmask[i];
-        while (v) { int bit = __ffs(v) - 1; v &= v - 1; s.vpos[ex++] = (uint16_t)(((wlo + i) << 5) + bit); }
+    for (int i = 0; i < K1_WPT; i++) {
+        const int w = tid * K1_WPT + i;
+        unsigned  m = 0;
+        if (w <= K1_TWORDS) {
+            unsigned prev = w ? (s.nl[w - 1] >> 31) : ((tile == 0) ? 1u : 0u);
+            m = ((s.nl[w] << 1) | prev) & ~s.nl[w];
+            if (w == K1_TWORDS) m &= 1u;
+        }
+        lsm[i] = m;
+        my_lines += __popc(m);
+    }
+    int n_lines, n_valid;
+    int lex = block_exclusive_sum<int, K1_THREADS>(my_lines, s.scan_ws, &n_lines);
+    __syncthreads();
+    if (n_lines <= K1_LCAP) {
+        // ---- A2 (dense): list the line starts, then one thread per line checks validity
+#pragma unroll
+        for (int i = 0; i < K1_WPT; i++) {
+            unsigned m = lsm[i];
+            while (m) { int bit = __ffs(m) - 1; m &= m - 1; s.lpos[lex++] = (uint16_t)(((tid * K1_WPT + i) << 5) + bit); }
+        }
+        __syncthreads();
+        int bad = 0;
+        for (int j = tid; j < n_lines; j += K1_THREADS) {
+            const int p = s.lpos[j];
+            if (is_record(p)) s.lpos[j] = (uint16_t)(p | 0x8000); else bad++;
+        }
+        if (bad) atomicAdd(&s.n_invalid, bad);
+        __syncthreads();
+        if (s.n_invalid == 0) {
+            // every line is a record (the usual case): the record list is the line list
+            for (int j = tid; j < n_lines; j += K1_THREADS) s.vpos[j] = (uint16_t)(s.lpos[j] & 0x7FFF);
+            n_valid = n_lines;
+        } else {
+            // order-preserving compaction: thread t owns list entries [t*C, (t+1)*C)
+            const int C = (n_lines + K1_THREADS - 1) / K1_THREADS; // <= 7
+            int       mine = 0;
+            for (int k = 0; k < C; k++) { int j = tid * C + k; if (j < n_lines && (s.lpos[j] & 0x8000)) mine++; }
+            int vex = block_exclusive_sum<int, K1_THREADS>(mine, s.scan_ws, &n_valid);
+            for (int k = 0; k < C; k++) { int j = tid * C + k; if (j < n_lines && (s.lpos[j] & 0x8000)) s.vpos[vex++] = (uint16_t)(s.lpos[j] & 0x7FFF); }
+        }
+    } else {
+        // ---- A2 (sparse, pathological tiles with > 1024 lines): every thread checks the lines of its own words
+        unsigned vm[K1_WPT];
+        int      mine = 0;
+#pragma unroll
+        for (int i = 0; i < K1_WPT; i++) {
+            unsigned m = lsm[i], v = 0;
+            while (m) { int bit = __ffs(m) - 1; m &= m - 1; if (is_record(((tid * K1_WPT + i) << 5) + bit)) v |= 1u << bit; }
+            vm[i] = v; mine += __popc(v);
+        }
+        int vex = block_exclusive_sum<int, K1_THREADS>(mine, s.scan_ws, &n_valid);
+#pragma unroll
+        for (int i = 0; i < K1_WPT; i++) {
+            unsigned v = vm[i];
+            while (v) { int bit = __ffs(v) - 1; v &= v - 1; s.vpos[vex++] = (uint16_t)(((tid * K1_WPT + i) << 5) + bit); }
+        }
     }
     if (tid == 0) lookback_publish(a.status, tile, (uint64_t)n_valid); // successors can look back while this tile decodes
     __syncthreads();
@@ -304,6 +371,7 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
 #pragma unroll
     for (int k = 0; k < 7; k++) r0[k] = a.rec0[k];
     const unsigned* sw = reinterpret_cast<const unsigned*>(s.text);
+    const unsigned* tw = reinterpret_cast<const unsigned*>(s.pad_front);
     uint64_t        prefix = 0;
     bool            have_prefix = false;
     for (int base = 0; base < n_valid || !have_prefix; base += K1_THREADS) {
@@ -327,9 +395,9 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k_paf_tokenize(PafTokArgs a)
             if (tp[8] < K1_STAGE) {
                 pr.qid = nametable_find(a.names, hash_name_smem(sw, p, tp[0], a.names.seed));
                 pr.tid = nametable_find(a.names, hash_name_smem(sw, tp[4] + 1, tp[5], a.names.seed));
-                pr.qs = parse_num_smem(s.text, tp[1] + 1, tp[2]); pr.qe = parse_num_smem(s.text, tp[2] + 1, tp[3]);
+                pr.qs = parse_num_smem(s.text, tw, tp[1] + 1, tp[2]); pr.qe = parse_num_smem(s.text, tw, tp[2] + 1, tp[3]);
                 pr.strand = (tp[4] > tp[3] + 1) && s.text[tp[3] + 1] == '-';
-                pr.ts = parse_num_smem(s.text, tp[6] + 1, tp[7]); pr.te = parse_num_smem(s.text, tp[7] + 1, tp[8]);
+                pr.ts = parse_num_smem(s.text, tw, tp[6] + 1, tp[7]); pr.te = parse_num_smem(s.text, tw, tp[7] + 1, tp[8]);
             } else { // the record runs past the staged bytes: byte-wise reader over global memory
                 rd.seek(t0 + p);
                 parse_record(rd, a.names, pr);
