@@ -101,7 +101,8 @@ struct raftgpu_ctx {
     DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
     DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
-    std::vector<int64_t> h_cov_tile_off, h_rep_line_off;
+    std::vector<int64_t> h_cov_tile_off, h_rep_line_off; // every OFF_SAMPLE-th entry of the device tables (+ the last)
+    DevBuf  b_off_sample;
     int64_t G = 0, n_repeats = 0, read_num_base = 0;
     raftgpu_stats stats{};
     DevBuf  b_stage[2];
@@ -122,6 +123,7 @@ struct raftgpu_ctx {
     std::vector<int64_t> h_frag_sample;  // (out_off, src_off) of every FRAG_SAMPLE-th record
     DevBuf         b_frag_sample;
 };
+constexpr int    OFF_SAMPLE = 256;
 constexpr size_t SEQ_CHUNK = 256ull << 20;
 constexpr int    FRAG_SAMPLE = 256;
 
@@ -821,17 +823,26 @@ static int layout_outputs(raftgpu_ctx* ctx)
     // tile byte counts were produced by the coverage scan (fused sizing)
     launch_scan_i32_to_i64(ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_off.as<int64_t>(), T, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
     CKL();
-    ctx->h_cov_tile_off.resize(T + 1); ctx->h_rep_line_off.resize(m + 1);
-    long long fasta_bytes = 0;
-    CK(cudaMemcpyAsync(ctx->h_cov_tile_off.data(), ctx->b_cov_tile_off.p, sizeof(int64_t) * (T + 1), cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(ctx->h_rep_line_off.data(), ctx->b_rep_line_off.p, sizeof(int64_t) * (m + 1), cudaMemcpyDeviceToHost, ctx->st));
+    // the host only needs a coarse view of the two offset tables (window -> tile / read range): every 256th entry
+    const size_t nc = (size_t)(T / OFF_SAMPLE + 2), nr = (size_t)(m / OFF_SAMPLE + 2);
+    ctx->h_cov_tile_off.resize(nc); ctx->h_rep_line_off.resize(nr);
+    CK(ctx->b_off_sample.ensure(sizeof(int64_t) * (nc + nr)));
+    launch_sample_i64(ctx->b_cov_tile_off.as<int64_t>(), T + 1, OFF_SAMPLE, ctx->b_off_sample.as<int64_t>(), ctx->st);
+    CKL();
+    launch_sample_i64(ctx->b_rep_line_off.as<int64_t>(), m + 1, OFF_SAMPLE, ctx->b_off_sample.as<int64_t>() + nc, ctx->st);
+    CKL();
+    long long fasta_bytes = 0, cov_bytes = 0, rep_bytes = 0;
+    CK(cudaMemcpyAsync(ctx->h_cov_tile_off.data(), ctx->b_off_sample.p, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_rep_line_off.data(), ctx->b_off_sample.as<int64_t>() + nc, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&cov_bytes, ctx->b_cov_tile_off.as<int64_t>() + T, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&rep_bytes, ctx->b_rep_line_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&fasta_bytes, ctx->b_frag_off.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, ctx->st));
     cudaEventRecord(ctx->ev[7], ctx->st);
     int st = fetch_err(ctx);
     if (st) return st;
     raftgpu_stats& s = ctx->stats;
-    s.out_bytes[RAFTGPU_OUT_COVERAGE] = (uint64_t)ctx->h_cov_tile_off[T];
-    s.out_bytes[RAFTGPU_OUT_LONG_REPEATS] = (uint64_t)ctx->h_rep_line_off[m];
+    s.out_bytes[RAFTGPU_OUT_COVERAGE] = (uint64_t)cov_bytes;
+    s.out_bytes[RAFTGPU_OUT_LONG_REPEATS] = (uint64_t)rep_bytes;
     s.out_bytes[RAFTGPU_OUT_BED] = 0; // real reads: the file is created empty (repeat.hpp:87,187)
     s.out_bytes[RAFTGPU_OUT_READS_FASTA] = (uint64_t)fasta_bytes;
     // record containing the first byte of every 16 KiB tile of reads.fasta
@@ -912,9 +923,12 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
 {
     const int64_t m = ctx->m;
     if (which == RAFTGPU_OUT_COVERAGE) {
+        // coarse tile range from the sampled offsets; tiles outside the window return early
         const auto& off = ctx->h_cov_tile_off;
-        int64_t t0 = std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1;
-        int64_t t1 = std::lower_bound(off.begin(), off.end(), w1) - off.begin();
+        const int64_t T = cov_tiles(ctx->n_slots);
+        int64_t t0 = (std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1) * OFF_SAMPLE;
+        int64_t t1 = (std::lower_bound(off.begin(), off.end(), w1) - off.begin()) * OFF_SAMPLE;
+        t0 = std::max<int64_t>(0, std::min(t0, T)); t1 = std::min(t1, T);
         CovEmitArgs ca{};
         ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
         ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
@@ -923,8 +937,9 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         CKL();
     } else if (which == RAFTGPU_OUT_LONG_REPEATS) {
         const auto& off = ctx->h_rep_line_off;
-        int64_t r0 = std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1;
-        int64_t r1 = std::lower_bound(off.begin(), off.end(), w1) - off.begin();
+        int64_t r0 = (std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1) * OFF_SAMPLE;
+        int64_t r1 = (std::lower_bound(off.begin(), off.end(), w1) - off.begin()) * OFF_SAMPLE;
+        r0 = std::max<int64_t>(0, std::min(r0, m));
         RepEmitArgs ra{};
         ra.rep_cnt = ctx->b_rep_cnt.as<int32_t>(); ra.rep_cap_off = ctx->b_rep_cap_off.as<int64_t>(); ra.rep = ctx->b_rep.as<int2>();
         ra.line_off = ctx->b_rep_line_off.as<int64_t>(); ra.m = m; ra.own_first = ctx->own_first; ra.dst = d; ra.w0 = w0; ra.w1 = w1;

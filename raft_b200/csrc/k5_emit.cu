@@ -453,6 +453,19 @@ void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
     k_fasta_emit<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);
 }
 
+__global__ void k_sample_i64(const int64_t* __restrict__ src, int64_t n, int step, int64_t cnt, int64_t* dst)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    int64_t i = k * step;
+    dst[k] = src[i < n ? i : n - 1];
+}
+void launch_sample_i64(const int64_t* src, int64_t n, int step, int64_t* dst, cudaStream_t st)
+{
+    int64_t cnt = (n - 1) / step + 2;
+    k_sample_i64<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(src, n, step, cnt, dst);
+}
+
 // ================================================================ digest
 __global__ void __launch_bounds__(256) k_digest(const uint8_t* __restrict__ buf, int64_t n, int64_t abs_off, unsigned long long* acc)
 {

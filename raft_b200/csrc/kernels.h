@@ -191,6 +191,8 @@ struct FastaEmitArgs {
 void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st);
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st);
 
+// dst[k] = src[min(k*step, n-1)] for k in [0, (n-1)/step + 1]  (coarse host-side copies of offset tables)
+void launch_sample_i64(const int64_t* src, int64_t n, int step, int64_t* dst, cudaStream_t st);
 void launch_digest(const uint8_t* buf, int64_t n, int64_t abs_off, unsigned long long* acc, cudaStream_t st);
 
 } // namespace raftk
