@@ -50,7 +50,8 @@ typedef enum {
     RAFTGPU_E_STATE = -9,        /* call order violated */
     RAFTGPU_E_IO = -10,          /* input file missing or empty (chop.hpp:336-349) / write failure */
     RAFTGPU_E_ARG = -11,         /* bad argument */
-    RAFTGPU_E_UNSUPPORTED = -12  /* simulated-read header mode on the device emitter (chop.hpp:252-258,293-310) */
+    RAFTGPU_E_UNSUPPORTED = -12,
+    RAFTGPU_E_SIM_NAME = -13     /* simulated-read mode (chop.hpp:99-106) but a name lacks the fields chop.hpp:14-70 dereference */
 } raftgpu_status;
 
 /* Output streams (files the reference writes: chop.hpp:333, repeat.hpp:85-87). */

@@ -102,7 +102,8 @@ struct raftgpu_ctx {
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
     DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
     std::vector<int64_t> h_cov_tile_off, h_rep_line_off; // every OFF_SAMPLE-th entry of the device tables (+ the last)
-    DevBuf  b_off_sample;
+    DevBuf  b_off_sample, b_sim, b_bed_line_size, b_bed_line_off;
+    std::vector<int64_t> h_bed_line_off;
     int64_t G = 0, n_repeats = 0, read_num_base = 0;
     raftgpu_stats stats{};
     DevBuf  b_stage[2];
@@ -179,6 +180,7 @@ const char* raftgpu_strerror(int s)
     case RAFTGPU_E_IO: return "input file missing/empty or output not writable";
     case RAFTGPU_E_ARG: return "bad argument";
     case RAFTGPU_E_UNSUPPORTED: return "not supported";
+    case RAFTGPU_E_SIM_NAME: return "simulated-read mode (first name matches read=N,align,position=a-b,length=L,chr) but a later name does not";
     default: return "unknown status";
     }
 }
@@ -370,6 +372,13 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
     }
     ctx->n_slots = tot[0]; ctx->rep_cap_total = tot[1]; ctx->cut_cap_total = tot[2];
     ctx->total_read_len = seq_total; // owned reads only (summed across ranks by the caller when sharded)
+    if (!ctx->real_reads) { // simulated-read names carry genome coordinates (chop.hpp:14-70): parse them once per owned read
+        CK(ctx->b_sim.ensure(sizeof(SimInfo) * (size_t)(m + 1)));
+        launch_sim_parse(ctx->d_names, ctx->d_name_off, ctx->own_first, m, ctx->b_sim.as<SimInfo>(), &ctx->misc()->err, ctx->st);
+        CKL();
+        int st = fetch_err(ctx);
+        if (st) return st;
+    }
     ctx->have_reads = true;
     return RAFTGPU_OK;
 }
@@ -805,7 +814,7 @@ static int layout_outputs(raftgpu_ctx* ctx)
     fa.cut_cap_off = ctx->b_cut_cap_off.as<int64_t>(); fa.cuts = ctx->b_cuts.as<int32_t>(); fa.frag_cnt = ctx->b_frag_cnt.as<int32_t>();
     fa.frag_base = ctx->b_frag_base.as<int64_t>(); fa.v = ctx->prm.overlap_length; fa.read_num_base = ctx->read_num_base;
     fa.frag_read = ctx->b_frag_read.as<int32_t>(); fa.frag_a = ctx->b_frag_a.as<int32_t>(); fa.frag_b = ctx->b_frag_b.as<int32_t>();
-    fa.frag_size = ctx->b_frag_size.as<int32_t>(); fa.err = &M->err;
+    fa.frag_size = ctx->b_frag_size.as<int32_t>(); fa.err = &M->err; fa.sim = ctx->real_reads ? nullptr : ctx->b_sim.as<SimInfo>();
     launch_frag_expand(fa, ctx->st);
     CKL();
     launch_scan_i32_to_i64(ctx->b_frag_size.as<int32_t>(), ctx->b_frag_off.as<int64_t>(), G, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
@@ -817,6 +826,15 @@ static int layout_outputs(raftgpu_ctx* ctx)
     CKL();
     launch_scan_i32_to_i64(ctx->b_rep_line_size.as<int32_t>(), ctx->b_rep_line_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
     CKL();
+    // long_repeats.bed lines (simulated reads only; the file is created empty otherwise, repeat.hpp:87,187)
+    if (!ctx->real_reads) {
+        CK(ctx->b_bed_line_size.ensure(sizeof(int32_t) * (size_t)(m + 1))); CK(ctx->b_bed_line_off.ensure(sizeof(int64_t) * (size_t)(m + 1)));
+        launch_bed_sizes(ctx->b_rep_cnt.as<int32_t>(), ctx->b_rep_cap_off.as<int64_t>(), ctx->b_rep.as<int2>(), ctx->b_sim.as<SimInfo>(),
+                         ctx->d_name_off, ctx->own_first, m, ctx->b_bed_line_size.as<int32_t>(), ctx->st);
+        CKL();
+        launch_scan_i32_to_i64(ctx->b_bed_line_size.as<int32_t>(), ctx->b_bed_line_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+        CKL();
+    }
     // coverage.txt tiles
     const int T = cov_tiles(ctx->n_slots);
     CK(ctx->b_cov_tile_off.ensure(sizeof(int64_t) * (size_t)(T + 1)));
@@ -831,7 +849,16 @@ static int layout_outputs(raftgpu_ctx* ctx)
     CKL();
     launch_sample_i64(ctx->b_rep_line_off.as<int64_t>(), m + 1, OFF_SAMPLE, ctx->b_off_sample.as<int64_t>() + nc, ctx->st);
     CKL();
-    long long fasta_bytes = 0, cov_bytes = 0, rep_bytes = 0;
+    long long fasta_bytes = 0, cov_bytes = 0, rep_bytes = 0, bed_bytes = 0;
+    if (!ctx->real_reads) {
+        ctx->h_bed_line_off.resize(nr);
+        DevBuf& bs = ctx->b_bed_line_size; // reuse as the sample target (sizes are no longer needed): nr int64 fit? ensure
+        CK(bs.ensure(sizeof(int64_t) * nr));
+        launch_sample_i64(ctx->b_bed_line_off.as<int64_t>(), m + 1, OFF_SAMPLE, bs.as<int64_t>(), ctx->st);
+        CKL();
+        CK(cudaMemcpyAsync(ctx->h_bed_line_off.data(), bs.p, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(&bed_bytes, ctx->b_bed_line_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    }
     CK(cudaMemcpyAsync(ctx->h_cov_tile_off.data(), ctx->b_off_sample.p, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(ctx->h_rep_line_off.data(), ctx->b_off_sample.as<int64_t>() + nc, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&cov_bytes, ctx->b_cov_tile_off.as<int64_t>() + T, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -843,7 +870,7 @@ static int layout_outputs(raftgpu_ctx* ctx)
     raftgpu_stats& s = ctx->stats;
     s.out_bytes[RAFTGPU_OUT_COVERAGE] = (uint64_t)cov_bytes;
     s.out_bytes[RAFTGPU_OUT_LONG_REPEATS] = (uint64_t)rep_bytes;
-    s.out_bytes[RAFTGPU_OUT_BED] = 0; // real reads: the file is created empty (repeat.hpp:87,187)
+    s.out_bytes[RAFTGPU_OUT_BED] = (uint64_t)bed_bytes; // real reads: the file is created empty (repeat.hpp:87,187)
     s.out_bytes[RAFTGPU_OUT_READS_FASTA] = (uint64_t)fasta_bytes;
     // record containing the first byte of every 16 KiB tile of reads.fasta
     CK(ctx->b_fasta_tile_frag.ensure(sizeof(int32_t) * (size_t)(fasta_bytes / FASTA_TILE + 2)));
@@ -946,9 +973,21 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         ra.read_first = r0; ra.read_last = std::min<int64_t>(r1, m);
         launch_rep_emit(ra, st);
         CKL();
+    } else if (which == RAFTGPU_OUT_BED) {
+        if (ctx->real_reads) return RAFTGPU_OK;
+        const auto& off = ctx->h_bed_line_off;
+        int64_t r0 = (std::upper_bound(off.begin(), off.end(), w0) - off.begin() - 1) * OFF_SAMPLE;
+        int64_t r1 = (std::lower_bound(off.begin(), off.end(), w1) - off.begin()) * OFF_SAMPLE;
+        r0 = std::max<int64_t>(0, std::min(r0, m));
+        RepEmitArgs ra{};
+        ra.rep_cnt = ctx->b_rep_cnt.as<int32_t>(); ra.rep_cap_off = ctx->b_rep_cap_off.as<int64_t>(); ra.rep = ctx->b_rep.as<int2>();
+        ra.line_off = ctx->b_bed_line_off.as<int64_t>(); ra.m = m; ra.own_first = ctx->own_first; ra.dst = d; ra.w0 = w0; ra.w1 = w1;
+        ra.read_first = r0; ra.read_last = std::min<int64_t>(r1, m);
+        ra.sim = ctx->b_sim.as<SimInfo>(); ra.names = ctx->d_names; ra.name_off = ctx->d_name_off;
+        launch_bed_emit(ra, st);
+        CKL();
     } else if (which == RAFTGPU_OUT_READS_FASTA) {
         if (!ctx->have_seq) FAIL(RAFTGPU_E_STATE, "reads.fasta requested but no sequence bytes were given");
-        if (!ctx->real_reads) FAIL(RAFTGPU_E_UNSUPPORTED, "simulated-read headers (chop.hpp:252-258,293-310) are not emitted by the device path");
         if (ctx->seq_host) {
             // arena bytes needed by stream window [w0, w1): records are in arena order, consecutive records of a
             // read overlap by at most overlap_length bytes
@@ -964,6 +1003,7 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         fa.desc = ctx->b_frag_desc.as<FragDesc>(); fa.G = ctx->G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
         fa.names = ctx->d_names; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first; fa.read_num_base = ctx->read_num_base;
         fa.dst = d; fa.w0 = w0; fa.w1 = w1; fa.tile_frag = ctx->b_fasta_tile_frag.as<int32_t>();
+        fa.sim = ctx->real_reads ? nullptr : ctx->b_sim.as<SimInfo>();
         // owned arenas are padded by 32 bytes; borrowed ones are only trusted up to their last whole 16-byte block
         fa.seq_safe_end = (ctx->d_seq == ctx->b_seq.as<uint8_t>()) ? ((ctx->total_read_len + 31) & ~(int64_t)15) : (ctx->total_read_len & ~(int64_t)15);
         launch_fasta_emit(fa, st);

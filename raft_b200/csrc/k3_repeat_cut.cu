@@ -130,6 +130,44 @@ void launch_repeat_cut(const RepeatCutArgs& a, cudaStream_t st)
     k_repeat_cut<<<(unsigned)blocks, K3_THREADS, 0, st>>>(a);
 }
 
+// ---------------------------------------------------------------- simulated-read names
+// chop.hpp:14-70: start = atoi after the first '=' that follows the first ','; end = atoi after the first '-';
+// align = between the first and second ','; chr / tail = from the last ','.
+__global__ void __launch_bounds__(256) k_sim_parse(const uint8_t* __restrict__ names, const int64_t* __restrict__ name_off, int64_t own_first,
+                                                    int64_t m, SimInfo* out, ErrState* err)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t  gid = own_first + i;
+    const uint8_t* s = names + name_off[gid];
+    const int      n = (int)(name_off[gid + 1] - name_off[gid]);
+    int c1 = -1, c2 = -1, eq = -1, da = -1, d0 = -1, c3 = -1, lc = -1;
+    for (int k = 0; k < n; k++) {
+        uint8_t c = s[k];
+        if (c == ',') { if (c1 < 0) c1 = k; else if (c2 < 0) c2 = k; if (d0 >= 0 && c3 < 0) c3 = k; lc = k; }
+        if (c == '=' && c1 >= 0 && eq < 0) eq = k;
+        if (c == '-') { if (d0 < 0) d0 = k; if (eq >= 0 && da < 0) da = k; }
+    }
+    SimInfo o{};
+    if (c1 < 0 || c2 < 0 || eq < 0 || da < 0 || d0 < 0 || c3 < 0) {
+        long long old = atomicMin(&err->index, (long long)gid);
+        if ((long long)gid <= old) err->code = RAFTK_E_SIM_NAME;
+        out[i] = o;
+        return;
+    }
+    auto atoi_range = [&](int a, int b) { long long v = 0; for (int k = a; k < b && s[k] >= '0' && s[k] <= '9'; k++) v = v * 10 + (s[k] - '0'); return (int)v; };
+    o.start_pos = atoi_range(eq + 1, da);
+    o.end_pos = atoi_range(d0 + 1, c3);
+    o.align_off = c1 + 1; o.align_len = c2 - c1 - 1; o.tail_off = lc;
+    auto is = [&](const char* w) { if (o.align_len != 7) return false; for (int k = 0; k < 7; k++) if (s[o.align_off + k] != (uint8_t)w[k]) return false; return true; };
+    o.flags = (is("forward") ? 1 : 0) | (is("reverse") ? 2 : 0);
+    out[i] = o;
+}
+void launch_sim_parse(const uint8_t* names, const int64_t* name_off, int64_t own_first, int64_t m, SimInfo* out, ErrState* err, cudaStream_t st)
+{
+    if (m > 0) k_sim_parse<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(names, name_off, own_first, m, out, err);
+}
+
 // ---------------------------------------------------------------- fragments
 // One thread per read: (a,b) of every fragment, the read= number, and the byte size of its FASTA
 // record  ">read=" num "," name ",pos_on_original_read=" a "-" b "\n" bases[a:b] "\n"  (chop.hpp:261-265,314-318).
@@ -154,7 +192,17 @@ __global__ void __launch_bounds__(256) k_frag_expand(FragExpandArgs a)
         int64_t g = g0 + j;
         a.frag_read[g] = (int32_t)i; a.frag_a[g] = (int32_t)fa; a.frag_b[g] = (int32_t)fb;
         int64_t num = a.read_num_base + g + 1;
-        int     hdr = 6 + dec_digits64((uint64_t)num) + 1 + name_len + 22 + dec_digits((uint32_t)fa) + 1 + dec_digits((uint32_t)fb) + 1;
+        int     hdr;
+        if (!a.sim) {
+            hdr = 6 + dec_digits64((uint64_t)num) + 1 + name_len + 22 + dec_digits((uint32_t)fa) + 1 + dec_digits((uint32_t)fb) + 1;
+        } else { // chop.hpp:252-258 (whole read), 293-310 (fragments: a header only for forward / reverse)
+            const SimInfo si = a.sim[i];
+            int x, y, ln;
+            sim_header_numbers(si, F == 1, (int)fa, (int)fb, (int)L, &x, &y, &ln);
+            hdr = (F == 1 || si.flags) ? 6 + dec_digits64((uint64_t)num) + 1 + si.align_len + 10 + dec_len_i32(x) + 1 + dec_len_i32(y) + 8 +
+                                             dec_len_i32(ln) + (name_len - si.tail_off) + 1
+                                       : 0;
+        }
         a.frag_size[g] = (int32_t)(hdr + (fb - fa) + 1);
     }
 }

@@ -190,6 +190,57 @@ void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st)
     if (cnt > 0) k_rep_emit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a);
 }
 
+// ---- long_repeats.bed (repeat.hpp:187-199): per repeat of a forward read  chr \t start+s \t start+e \n,
+// of a reverse read  chr \t end-e \t end-s \n; other orientations write nothing.
+__device__ __forceinline__ void bed_numbers(const SimInfo& si, int2 r, int* x, int* y)
+{
+    if (si.flags & 1) { *x = si.start_pos + r.x; *y = si.start_pos + r.y; }
+    else { *x = si.end_pos - r.y; *y = si.end_pos - r.x; }
+}
+__global__ void __launch_bounds__(256) k_bed_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, const SimInfo* sim,
+                                                    const int64_t* name_off, int64_t own_first, int64_t m, int32_t* line_size)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const SimInfo si = sim[i];
+    int           sz = 0;
+    if (si.flags) {
+        const int   chr_len = (int)(name_off[own_first + i + 1] - name_off[own_first + i]) - si.tail_off - 1;
+        const int2* r = rep + rep_cap_off[i];
+        for (int q = 0; q < rep_cnt[i]; q++) { int x, y; bed_numbers(si, r[q], &x, &y); sz += chr_len + 1 + dec_len_i32(x) + 1 + dec_len_i32(y) + 1; }
+    }
+    line_size[i] = sz;
+}
+void launch_bed_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, const SimInfo* sim, const int64_t* name_off,
+                      int64_t own_first, int64_t m, int32_t* line_size, cudaStream_t st)
+{
+    if (m > 0) k_bed_sizes<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(rep_cnt, rep_cap_off, rep, sim, name_off, own_first, m, line_size);
+}
+__global__ void __launch_bounds__(256) k_bed_emit(RepEmitArgs a)
+{
+    int64_t i = a.read_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.read_last) return;
+    int64_t o0 = a.line_off[i], o1 = a.line_off[i + 1];
+    if (o1 <= a.w0 || o0 >= a.w1 || o1 == o0) return;
+    const SimInfo  si = a.sim[i];
+    const int64_t  nm0 = a.name_off[a.own_first + i];
+    const int      chr_len = (int)(a.name_off[a.own_first + i + 1] - nm0) - si.tail_off - 1;
+    const uint8_t* chr = a.names + nm0 + si.tail_off + 1;
+    WinWriter      w{a.dst, a.w0, a.w1, o0};
+    const int2*    r = a.rep + a.rep_cap_off[i];
+    for (int q = 0; q < a.rep_cnt[i]; q++) {
+        int x, y;
+        bed_numbers(si, r[q], &x, &y);
+        for (int k = 0; k < chr_len; k++) w.put(chr[k]);
+        w.put('\t'); w.put_i32(x); w.put('\t'); w.put_i32(y); w.put('\n');
+    }
+}
+void launch_bed_emit(const RepEmitArgs& a, cudaStream_t st)
+{
+    int64_t cnt = a.read_last - a.read_first;
+    if (cnt > 0) k_bed_emit<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a);
+}
+
 // ================================================================ K5b reads.fasta
 // Output-tile-parallel gather, persistent and warp-specialised.  A tile is 16 KiB of the reads.fasta stream.
 // Warp 0 (one lane) is the producer: for each tile it walks the records that intersect it (tile_frag[T] gives
@@ -412,23 +463,54 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
             if (hp0 < hp1) {
                 const int64_t  gid = a.own_first + pc.read;
                 const uint64_t num = (uint64_t)(a.read_num_base + pc.frag + 1);
-                const unsigned fa = (unsigned)pc.fa, fb = (unsigned)(pc.fa + pc.len);
                 const int64_t  nm0 = a.name_off[gid];
                 const int      nl = (int)(a.name_off[gid + 1] - nm0);
-                const int      dn = dec_digits64(num), da = dec_digits(fa), db = dec_digits(fb);
-                for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
-                    int     q = (int)(x - O);
-                    uint8_t c;
-                    if (q < 6) c = (uint8_t)(">read="[q]);
-                    else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
-                    else if ((q -= dn) < 1) c = ',';
-                    else if ((q -= 1) < nl) c = a.names[nm0 + q];
-                    else if ((q -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[q]);
-                    else if ((q -= 22) < da) c = dec_digit_at32(fa, da, q);
-                    else if ((q -= da) < 1) c = '-';
-                    else if ((q -= 1) < db) c = dec_digit_at32(fb, db, q);
-                    else c = '\n';
-                    a.dst[x - a.w0] = c;
+                const int      dn = dec_digits64(num);
+                if (!a.sim) {
+                    const unsigned fa = (unsigned)pc.fa, fb = (unsigned)(pc.fa + pc.len);
+                    const int      da = dec_digits(fa), db = dec_digits(fb);
+                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
+                        int     q = (int)(x - O);
+                        uint8_t c;
+                        if (q < 6) c = (uint8_t)(">read="[q]);
+                        else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
+                        else if ((q -= dn) < 1) c = ',';
+                        else if ((q -= 1) < nl) c = a.names[nm0 + q];
+                        else if ((q -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[q]);
+                        else if ((q -= 22) < da) c = dec_digit_at32(fa, da, q);
+                        else if ((q -= da) < 1) c = '-';
+                        else if ((q -= 1) < db) c = dec_digit_at32(fb, db, q);
+                        else c = '\n';
+                        a.dst[x - a.w0] = c;
+                    }
+                } else {
+                    // ">read=" num "," align ",position=" x "-" y ",length=" ln tail "\n"   (chop.hpp:252-258, 293-310)
+                    const SimInfo si = a.sim[pc.read];
+                    const int     L = (int)(a.seq_off[pc.read + 1] - a.seq_off[pc.read]);
+                    int           vx, vy, vl;
+                    sim_header_numbers(si, pc.len == L && pc.fa == 0, pc.fa, pc.fa + pc.len, L, &vx, &vy, &vl);
+                    const int dx = dec_len_i32(vx), dy = dec_len_i32(vy), dl = dec_len_i32(vl), tl = nl - si.tail_off;
+                    auto signed_char_at = [](int v, int nd, int q) -> uint8_t {
+                        if (v < 0) { if (q == 0) return '-'; return dec_digit_at32((uint32_t)(-(int64_t)v), nd - 1, q - 1); }
+                        return dec_digit_at32((uint32_t)v, nd, q);
+                    };
+                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
+                        int     q = (int)(x - O);
+                        uint8_t c;
+                        if (q < 6) c = (uint8_t)(">read="[q]);
+                        else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
+                        else if ((q -= dn) < 1) c = ',';
+                        else if ((q -= 1) < si.align_len) c = a.names[nm0 + si.align_off + q];
+                        else if ((q -= si.align_len) < 10) c = (uint8_t)(",position="[q]);
+                        else if ((q -= 10) < dx) c = signed_char_at(vx, dx, q);
+                        else if ((q -= dx) < 1) c = '-';
+                        else if ((q -= 1) < dy) c = signed_char_at(vy, dy, q);
+                        else if ((q -= dy) < 8) c = (uint8_t)(",length="[q]);
+                        else if ((q -= 8) < dl) c = signed_char_at(vl, dl, q);
+                        else if ((q -= dl) < tl) c = a.names[nm0 + si.tail_off + q];
+                        else c = '\n';
+                        a.dst[x - a.w0] = c;
+                    }
                 }
             }
             const int64_t s1 = O + h + pc.len;

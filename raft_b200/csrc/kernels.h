@@ -9,7 +9,7 @@
 namespace raftk {
 
 // device-side error codes (same numbering as raftgpu_status)
-enum { RAFTK_E_UNKNOWN_NAME = -2, RAFTK_E_DUP_NAME = -3, RAFTK_E_RANGE = -4, RAFTK_E_NEG_START = -5, RAFTK_E_HASH_COLLISION = -100 };
+enum { RAFTK_E_UNKNOWN_NAME = -2, RAFTK_E_DUP_NAME = -3, RAFTK_E_RANGE = -4, RAFTK_E_NEG_START = -5, RAFTK_E_SIM_NAME = -13, RAFTK_E_HASH_COLLISION = -100 };
 
 struct ErrState {
     long long index; // smallest offending record / read index (LLONG_MAX when clean)
@@ -106,6 +106,25 @@ struct RepeatCutArgs {
 };
 void launch_repeat_cut(const RepeatCutArgs& a, cudaStream_t st);
 
+// Simulated-read names "read=N,forward|reverse,position=a-b,length=L,chr" (chop.hpp:14-70): what the header /
+// BED variants need, parsed once per owned read.
+struct __align__(16) SimInfo {
+    int start_pos, end_pos;      // chop.hpp:25-47
+    int align_off, align_len;    // chop.hpp:49-59, name relative
+    int tail_off;                // offset of the last ',' (read_name.substr(find_last_of(',')), chop.hpp:257)
+    int flags;                   // 1 forward, 2 reverse
+    int pad[2];
+};
+// the three numbers of a simulated-read header: position=x-y,length=ln
+__device__ __forceinline__ void sim_header_numbers(const SimInfo& si, bool whole, int fa, int fb, int L, int* x, int* y, int* ln)
+{
+    if (whole) { *x = si.start_pos; *y = si.end_pos; *ln = L; }
+    else if (si.flags & 1) { *x = si.start_pos + fa; *y = si.start_pos + fb; *ln = fb - fa; }
+    else { *x = si.end_pos - fb; *y = si.end_pos - fa; *ln = fb - fa; }
+}
+
+void launch_sim_parse(const uint8_t* names, const int64_t* name_off, int64_t own_first, int64_t m, SimInfo* out, ErrState* err, cudaStream_t st);
+
 struct FragExpandArgs {
     int64_t        m;
     const int64_t* seq_off;     // local, m+1
@@ -120,6 +139,7 @@ struct FragExpandArgs {
     int32_t *      frag_read, *frag_a, *frag_b; // G
     int32_t*       frag_size;   // G: bytes of the FASTA record
     ErrState*      err;
+    const SimInfo* sim;         // null for real reads
 };
 void launch_frag_expand(const FragExpandArgs& a, cudaStream_t st);
 // compact repeats: rep_off = exclusive scan of rep_cnt; rep_out[2*k] pairs in read order; also text size per read line
@@ -149,6 +169,9 @@ int  cov_tiles(int64_t n_slots);
 void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st);
 void launch_cov_emit(const CovEmitArgs& a, int64_t n_tiles_launch, cudaStream_t st);
 
+// long_repeats.bed (simulated reads only, repeat.hpp:187-199): chr \t x \t y \n per repeat
+void launch_bed_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, const SimInfo* sim, const int64_t* name_off,
+                      int64_t own_first, int64_t m, int32_t* line_size, cudaStream_t st);
 struct RepEmitArgs {
     const int32_t* rep_cnt;
     const int64_t* rep_cap_off;
@@ -158,7 +181,11 @@ struct RepEmitArgs {
     uint8_t*       dst;
     int64_t        w0, w1;
     int64_t        read_first, read_last; // local read range to emit
+    const SimInfo* sim;      // BED variant when non-null (with names / name_off)
+    const uint8_t* names;
+    const int64_t* name_off;
 };
+void launch_bed_emit(const RepEmitArgs& a, cudaStream_t st);
 void launch_rep_emit(const RepEmitArgs& a, cudaStream_t st);
 
 constexpr int FASTA_TILE = 16384;
@@ -187,6 +214,7 @@ struct FastaEmitArgs {
     int64_t        w0, w1;   // stream window; CTA b covers stream bytes [(w0/TILE + b)*TILE, +TILE) clipped to it
     const int32_t* tile_frag; // record containing stream byte T*FASTA_TILE, for every tile of the stream
     int64_t        seq_safe_end; // bytes of the arena that may be read in 16-byte blocks (multiple of 16)
+    const SimInfo* sim;          // null for real reads
 };
 void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st);
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st);

@@ -10,6 +10,7 @@ import pytest
 from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
 from oracle import oracle as O
 from raft_b200 import api, synth
+from sim_util import sim_dataset
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,14 +50,13 @@ def compare_all(ctx, st, ref, real=True):
         ref.total_cov, ref.total_windows, ref.total_repeat_len, ref.total_read_len)
     assert ctx.fetch(api.OUT_COVERAGE) == ref.cov_txt
     assert ctx.fetch(api.OUT_LONG_REPEATS) == ref.rep_txt
-    if real:
-        assert ctx.fetch(api.OUT_READS_FASTA) == ref.fasta
-        assert ctx.fetch(api.OUT_BED) == ref.bed_txt
-        for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta)):
-            assert ctx.digest(which) == O.digest(data)
+    assert ctx.fetch(api.OUT_READS_FASTA) == ref.fasta
+    assert ctx.fetch(api.OUT_BED) == ref.bed_txt
+    for which, data in ((api.OUT_COVERAGE, ref.cov_txt), (api.OUT_LONG_REPEATS, ref.rep_txt), (api.OUT_READS_FASTA, ref.fasta), (api.OUT_BED, ref.bed_txt)):
+        assert ctx.digest(which) == O.digest(data)
 
 
-@pytest.mark.parametrize("entry", [e for e in CASES if e["name"] != "sim"], ids=lambda e: e["name"])
+@pytest.mark.parametrize("entry", CASES, ids=lambda e: e["name"])
 def test_golden_through_c_abi(entry):
     """Outputs equal the reference binary's committed outputs (tests/golden)."""
     fa, paf = load_inputs(entry)
@@ -69,6 +69,20 @@ def test_golden_through_c_abi(entry):
     assert stdout_value(entry, "length of alignments") == f"INFO, length of alignments  {st.n_records}()"
     assert stdout_value(entry, "high_cov") == f"high_cov {st.high_cov}"
     compare_all(ctx, st, O.run(reads, paf, O.make_params(**kw)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_simulated_read_mode(seed):
+    """Header variant and long_repeats.bed for simulated reads (chop.hpp:252-258,293-310; repeat.hpp:187-199)."""
+    reads, paf = sim_dataset(seed)
+    kw = dict(est_cov=30, repeat_length=4000, read_length=8000, flanking_length=300, overlap_length=200)
+    ref = O.run(reads, paf, O.make_params(**kw))
+    assert ref.status == 0 and ref.real_reads == 0 and len(ref.bed_txt) > 0 and ref.n_frag > reads.n
+    ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
+    compare_all(ctx, st, ref)
+    total = ctx.output_size(api.OUT_BED)
+    assert ctx.fetch(api.OUT_BED, 3, min(1000, total - 3)) == ref.bed_txt[3:3 + min(1000, total - 3)]
     ctx.close()
 
 
@@ -159,8 +173,6 @@ def test_cli_binary_against_golden():
     exe = os.path.join(ROOT, "raft_b200", "raft")
     assert os.path.exists(exe), "run make"
     for entry in CASES:
-        if entry["name"] in ("sim",):
-            continue
         fa, paf = load_inputs(entry)
         with tempfile.TemporaryDirectory() as d:
             open(os.path.join(d, "r.fa"), "wb").write(fa)

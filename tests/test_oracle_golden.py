@@ -7,6 +7,7 @@ import pytest
 from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
 from oracle import oracle as O
 from raft_b200 import synth
+from sim_util import sim_dataset
 
 CASES = manifest()
 
@@ -71,3 +72,18 @@ def test_digest_is_window_additive():
     whole = O.digest(data)
     parts = (O.digest(data[:100], 0) + O.digest(data[100:1000], 100) + O.digest(data[1000:], 1000)) & (2**64 - 1)
     assert whole == parts
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/raft not built (reference sources not mounted)")
+def test_oracle_sim_mode_matches_reference_binary_live():
+    reads, paf = sim_dataset(5)
+    with tempfile.TemporaryDirectory() as d:
+        fa, pf = os.path.join(d, "r.fa"), os.path.join(d, "o.paf")
+        open(fa, "wb").write(synth.format_fasta(reads, wrap=60))
+        open(pf, "wb").write(paf)
+        rc, out, files = O.run_ref(fa, pf, d, ["-e", "30", "-p", "4000", "-l", "8000", "-f", "300", "-v", "200"])
+    assert rc == 0 and "Real Reads 0 " in out
+    res = O.run(reads, paf, O.make_params(est_cov=30, repeat_length=4000, read_length=8000, flanking_length=300, overlap_length=200))
+    assert res.status == 0 and res.real_reads == 0 and len(res.bed_txt) > 0
+    for suf, data in zip(SUFS, (res.cov_txt, res.rep_txt, res.bed_txt, res.fasta)):
+        assert files.get(suf, b"") == data, suf
