@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
 SRC       := raft_b200/csrc
 OBJ       := build
-CU        := nametable k1_paf k2_coverage k3_repeat_cut k5_emit api
+CU        := nametable k0_fasta k1_paf k2_coverage k3_repeat_cut k5_emit api
 OBJS      := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/host_io.o
 LIB       := raft_b200/libraft_b200.so
 

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libraft_b200.so")
 # every symbol include/raft_b200.h declares
 SYMBOLS = [
     "raftgpu_default_params", "raftgpu_create", "raftgpu_destroy", "raftgpu_reset", "raftgpu_strerror",
-    "raftgpu_last_error", "raftgpu_error_index", "raftgpu_set_option", "raftgpu_set_reads", "raftgpu_load_fasta", "raftgpu_free_host",
+    "raftgpu_last_error", "raftgpu_error_index", "raftgpu_set_option", "raftgpu_set_reads", "raftgpu_ingest_fasta", "raftgpu_load_fasta", "raftgpu_free_host",
     "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_digest",
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
@@ -59,6 +59,7 @@ def lib():
         "raftgpu_error_index": (i64, [vp]),
         "raftgpu_set_option": (C.c_int, [vp, C.c_int, i64]),
         "raftgpu_set_reads": (C.c_int, [vp, i64, vp, vp, vp, vp]),
+        "raftgpu_ingest_fasta": (C.c_int, [vp, vp, sz, C.c_int, u64]),
         "raftgpu_load_fasta": (C.c_int, [C.c_char_p, C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "raftgpu_free_host": (None, [vp]),
         "raftgpu_ingest_paf": (C.c_int, [vp, vp, sz, C.c_int]),

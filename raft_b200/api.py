@@ -116,6 +116,13 @@ class Context:
         n = len(seq_off) - 1
         self._ck(self.L.raftgpu_set_reads(self._h, n, _ptr(seq_off), _ptr(seq), _ptr(name_off), _ptr(names)))
 
+    def ingest_fasta(self, text, nbytes=None, last=True, total_hint=0):
+        """Device FASTA tokenizer (loadFASTA's record grammar, chop.hpp:88-131); raises RaftError(-12) for FASTQ / CRLF text."""
+        if nbytes is None:
+            nbytes = len(text) if not hasattr(text, "numel") else text.numel()
+        self._keep.append(text)
+        self._ck(self.L.raftgpu_ingest_fasta(self._h, _ptr(text), nbytes, 1 if last else 0, total_hint))
+
     def set_reads_sharded(self, n, lengths, name_off, names, own_first, own_count, own_seq_off, own_seq):
         self._keep = [lengths, name_off, names, own_seq_off, own_seq]
         self._ck(self.L.raftgpu_set_reads_sharded(self._h, n, _ptr(lengths), _ptr(name_off), _ptr(names), own_first,

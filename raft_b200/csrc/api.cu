@@ -58,6 +58,9 @@ struct Misc {
     unsigned long long stats[2];
     unsigned long long digest;
     unsigned long long route_counts[64];
+    int                fa_flags;
+    int                fa_pad;
+    long long          fa_totals[2];
 };
 
 constexpr size_t WINDOW_BYTES = 256ull << 20; // staging window for host fetches
@@ -112,6 +115,12 @@ struct raftgpu_ctx {
     cudaEvent_t ev_emit[2]{};
     bool        emit_pending = false;
     int         emit_pending_which = 0;
+
+    // device FASTA ingest (raftgpu_ingest_fasta)
+    bool    fasta_active = false;
+    int64_t fa_n = 0, fa_bases = 0, fa_name_bytes = 0, fa_rec_cap = 0;
+    std::vector<uint8_t> fa_carry;
+    DevBuf  b_fa_text, b_fa_rec_pos, b_fa_name_len, b_fa_name_off_chunk, b_fa_status;
 
     // deferred sequence upload (RAFTGPU_OPT_DEFER_SEQ_UPLOAD)
     bool           opt_defer_seq = false;
@@ -241,6 +250,7 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     ctx->n_rec = 0; ctx->carry.clear(); ctx->first_is_local = true; ctx->rec0_external = ctx->sym_external = false;
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
     ctx->q_scattered = false; ctx->h_sym = 0;
+    ctx->fasta_active = false; ctx->fa_n = ctx->fa_bases = ctx->fa_name_bytes = 0; ctx->fa_carry.clear();
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
     ctx->emit_pending = false;
@@ -456,6 +466,131 @@ extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int6
     std::string first;
     if ((st = first_name_of(ctx, n, name_off, names, first))) return st;
     st = build_layout_and_names(ctx, first);
+    cudaEventRecord(ctx->ev[1], ctx->st);
+    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_set_reads, ctx->ev[0], ctx->ev[1]);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------ device FASTA ingest
+static int fasta_chunk(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len, bool first, bool last)
+{
+    if (len <= 0) return RAFTGPU_OK;
+    Misc*     M = ctx->misc();
+    const int tiles = fasta_tokenize_tiles(len);
+    CK(ctx->b_fa_status.ensure(sizeof(uint64_t) * 3 * (size_t)(tiles + 8)));
+    CK(ctx->b_seq.ensure((size_t)(ctx->fa_bases + len) + 64, (size_t)ctx->fa_bases, ctx->st)); // arena: at most one byte per text byte
+    int64_t want_cap = len / 512 + 1024;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int64_t need = ctx->fa_n + want_cap + 1;
+        if (need > ctx->fa_rec_cap) {
+            int64_t cap = need + need / 4;
+            CK(ctx->b_seq_off.ensure(sizeof(int64_t) * (size_t)(cap + 1), sizeof(int64_t) * (size_t)ctx->fa_n, ctx->st));
+            CK(ctx->b_name_off.ensure(sizeof(int64_t) * (size_t)(cap + 1), sizeof(int64_t) * (size_t)ctx->fa_n, ctx->st));
+            ctx->fa_rec_cap = cap;
+        }
+        CK(ctx->b_fa_rec_pos.ensure(sizeof(int64_t) * (size_t)(want_cap + 1)));
+        CK(cudaMemsetAsync(ctx->b_fa_status.p, 0, sizeof(uint64_t) * 3 * (size_t)tiles, ctx->st));
+        CK(cudaMemsetAsync(&M->ticket, 0, sizeof(int), ctx->st));
+        CK(cudaMemsetAsync(&M->fa_flags, 0, sizeof(int) * 2 + sizeof(long long) * 2, ctx->st));
+        FastaTokArgs a{};
+        a.text = dtext; a.nbytes = len; a.n_tiles = tiles; a.first_chunk = first; a.last_chunk = last;
+        a.seq_out = ctx->b_seq.as<uint8_t>() + ctx->fa_bases; a.seq_off_base = ctx->fa_bases;
+        a.rec_pos = ctx->b_fa_rec_pos.as<int64_t>(); a.seq_off = ctx->b_seq_off.as<int64_t>() + ctx->fa_n; a.rec_cap = want_cap;
+        a.st_carry = ctx->b_fa_status.as<uint64_t>(); a.st_keep = a.st_carry + tiles; a.st_rec = a.st_keep + tiles;
+        a.ticket = &M->ticket; a.flags = &M->fa_flags; a.totals = M->fa_totals;
+        CK(launch_fasta_tokenize(a, ctx->st));
+        ctx->launches++;
+        struct { int flags, pad; long long tot[2]; } h;
+        CK(cudaMemcpyAsync(&h, &M->fa_flags, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (h.flags) FAIL(RAFTGPU_E_UNSUPPORTED, "FASTA text needs the host reader (FASTQ '+' line, CR LF line ends, or no leading '>' / '@')");
+        if (h.tot[0] > want_cap) { want_cap = h.tot[0]; continue; } // more records than the optimistic capacity: redo this chunk
+        const int64_t nrec = h.tot[0];
+        // names of this chunk's records
+        CK(ctx->b_fa_name_len.ensure(sizeof(int32_t) * (size_t)(nrec + 1)));
+        CK(ctx->b_fa_name_off_chunk.ensure(sizeof(int64_t) * (size_t)(nrec + 2)));
+        CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_small(nrec) + 8)));
+        launch_fasta_name_len(dtext, len, ctx->b_fa_rec_pos.as<int64_t>(), nrec, ctx->b_fa_name_len.as<int32_t>(), ctx->st);
+        CKL();
+        launch_scan_i32_to_i64(ctx->b_fa_name_len.as<int32_t>(), ctx->b_fa_name_off_chunk.as<int64_t>(), nrec, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+        CKL();
+        long long nb = 0;
+        CK(cudaMemcpyAsync(&nb, ctx->b_fa_name_off_chunk.as<int64_t>() + nrec, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(ctx->b_names.ensure((size_t)(ctx->fa_name_bytes + nb) + 64, (size_t)ctx->fa_name_bytes, ctx->st));
+        launch_fasta_name_copy(dtext, ctx->b_fa_rec_pos.as<int64_t>(), ctx->b_fa_name_off_chunk.as<int64_t>(), nrec,
+                               ctx->b_names.as<uint8_t>() + ctx->fa_name_bytes, ctx->st);
+        CKL();
+        // global name offsets of these records = chunk offsets + bytes so far
+        launch_add_offset_i64(ctx->b_fa_name_off_chunk.as<int64_t>(), nrec, ctx->fa_name_bytes, ctx->b_name_off.as<int64_t>() + ctx->fa_n, ctx->st);
+        CKL();
+        CK(cudaStreamSynchronize(ctx->st));
+        ctx->fa_n += nrec; ctx->fa_bases += h.tot[1]; ctx->fa_name_bytes += nb;
+        return RAFTGPU_OK;
+    }
+    FAIL(RAFTGPU_E_STATE, "FASTA record capacity retry failed");
+}
+
+extern "C" int raftgpu_ingest_fasta(raftgpu_ctx* ctx, const uint8_t* text, size_t nbytes, int last_chunk, uint64_t total_hint)
+{
+    if (!ctx || (!text && nbytes)) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int st;
+    const bool first = !ctx->fasta_active;
+    if (first) {
+        if ((st = raftgpu_reset(ctx))) return st;
+        ctx->fasta_active = true; ctx->fa_rec_cap = 0;
+        cudaEventRecord(ctx->ev[0], ctx->st);
+        if (total_hint) CK(ctx->b_seq.ensure((size_t)total_hint + 64));
+    }
+    const bool   dev = nbytes && is_device_ptr(text);
+    const size_t total = ctx->fa_carry.size() + nbytes;
+    const uint8_t* dtext = nullptr;
+    if (dev && ctx->fa_carry.empty() && ((uintptr_t)text & 15) == 0) {
+        dtext = text;
+    } else if (total) {
+        CK(ctx->b_fa_text.ensure(total + 64));
+        uint8_t* d = ctx->b_fa_text.as<uint8_t>();
+        if (!ctx->fa_carry.empty()) CK(cudaMemcpyAsync(d, ctx->fa_carry.data(), ctx->fa_carry.size(), cudaMemcpyHostToDevice, ctx->st));
+        if (nbytes) CK(cudaMemcpyAsync(d + ctx->fa_carry.size(), text, nbytes, cudaMemcpyDefault, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        dtext = d;
+    }
+    size_t proc = total;
+    if (!last_chunk && total) { // hold back the unterminated last line
+        size_t scan = std::min<size_t>(total, 1 << 20);
+        std::vector<uint8_t> tail;
+        long long nlpos = -1;
+        for (;;) {
+            tail.resize(scan);
+            CK(cudaMemcpy(tail.data(), dtext + (total - scan), scan, cudaMemcpyDeviceToHost));
+            for (long long k = (long long)scan - 1; k >= 0; k--) if (tail[k] == '\n') { nlpos = (long long)(total - scan) + k; break; }
+            if (nlpos >= 0 || scan == total) break;
+            scan = std::min<size_t>(total, scan * 8);
+        }
+        proc = (size_t)(nlpos + 1);
+        ctx->fa_carry.assign(tail.begin() + (proc - (total - scan)), tail.end());
+    } else ctx->fa_carry.clear();
+    st = fasta_chunk(ctx, dtext, (int64_t)proc, first, last_chunk != 0);
+    if (st) { raftgpu_reset(ctx); return st; }
+    if (!last_chunk) return RAFTGPU_OK;
+    // ---- all records are in: close the offset arrays and continue exactly like raftgpu_set_reads
+    const int64_t n = ctx->fa_n;
+    if (n > 0x7ffffff0ll) { raftgpu_reset(ctx); return RAFTGPU_E_ARG; }
+    if (ctx->fa_rec_cap < n + 1) { // empty input: nothing was allocated yet
+        CK(ctx->b_seq_off.ensure(sizeof(int64_t) * 2)); CK(ctx->b_name_off.ensure(sizeof(int64_t) * 2)); CK(ctx->b_seq.ensure(64)); CK(ctx->b_names.ensure(64));
+    }
+    CK(cudaMemcpy(ctx->b_seq_off.as<int64_t>() + n, &ctx->fa_bases, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->b_name_off.as<int64_t>() + n, &ctx->fa_name_bytes, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemsetAsync(ctx->b_seq.as<uint8_t>() + ctx->fa_bases, 0, 32, ctx->st));
+    ctx->fasta_active = false;
+    ctx->n = n; ctx->m = n; ctx->own_first = 0;
+    ctx->d_seq_off = ctx->b_seq_off.as<int64_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
+    ctx->d_name_off = ctx->b_name_off.as<int64_t>(); ctx->d_names = ctx->b_names.as<uint8_t>();
+    ctx->have_seq = true;
+    std::string first_name;
+    if ((st = first_name_of(ctx, n, ctx->d_name_off, ctx->d_names, first_name))) return st;
+    st = build_layout_and_names(ctx, first_name);
     cudaEventRecord(ctx->ev[1], ctx->st);
     if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_set_reads, ctx->ev[0], ctx->ev[1]);
     return st;

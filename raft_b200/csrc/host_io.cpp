@@ -3,6 +3,8 @@
 // through the C ABI in include/raft_b200.h.
 #include <zlib.h>
 
+#include <algorithm>
+
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -209,14 +211,42 @@ extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* pa
         return code;
     };
 
-    int64_t  n = 0;
-    int64_t *seq_off = nullptr, *name_off = nullptr;
-    uint8_t *seq = nullptr, *names = nullptr;
-    if ((st = raftgpu_load_fasta(readfilename, &n, &seq_off, &seq, &name_off, &names))) return fail(st);
-    st = raftgpu_set_reads(ctx, n, seq_off, seq, name_off, names);
-    free(seq_off); free(seq); free(name_off); free(names);
+    // reads: plain FASTA text is tokenised on the device; gzip, FASTQ and CR LF text go through the host reader
+    bool on_device = false;
+    {
+        FILE* f = fopen(readfilename, "rb");
+        if (!f) return fail(RAFTGPU_E_IO);
+        unsigned char magic[2] = {0, 0};
+        size_t        got = fread(magic, 1, 2, f);
+        if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+            fseeko(f, 0, SEEK_END);
+            const uint64_t fsize = (uint64_t)ftello(f);
+            fseeko(f, 0, SEEK_SET);
+            std::vector<uint8_t> buf(std::min<uint64_t>(256u << 20, fsize ? fsize : 1));
+            uint64_t done = 0;
+            st = RAFTGPU_OK;
+            while (st == RAFTGPU_OK) {
+                size_t r = fread(buf.data(), 1, buf.size(), f);
+                done += r;
+                const bool last = done >= fsize || r == 0;
+                st = raftgpu_ingest_fasta(ctx, buf.data(), r, last ? 1 : 0, fsize);
+                if (last) break;
+            }
+            if (st == RAFTGPU_OK) on_device = true;
+            else if (st != RAFTGPU_E_UNSUPPORTED) { fclose(f); return fail(st); }
+        }
+        fclose(f);
+    }
     raftgpu_stats s{};
-    if (st) return fail(st);
+    if (!on_device) {
+        int64_t  n = 0;
+        int64_t *seq_off = nullptr, *name_off = nullptr;
+        uint8_t *seq = nullptr, *names = nullptr;
+        if ((st = raftgpu_load_fasta(readfilename, &n, &seq_off, &seq, &name_off, &names))) return fail(st);
+        st = raftgpu_set_reads(ctx, n, seq_off, seq, name_off, names);
+        free(seq_off); free(seq); free(name_off); free(names);
+        if (st) return fail(st);
+    }
 
     // PAF: inflate (or read) in chunks and hand them to the tokenizer (paf.hpp:24-38 uses gzopen/gzread too)
     {

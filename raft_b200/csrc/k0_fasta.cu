@@ -1,0 +1,296 @@
+// k0_fasta.cu — K0: FASTA tokenizer on the device.
+//
+// Replaces the record reader behind loadFASTA (chop.hpp:88-131, kseq_read kseq.h:240-298) for plain FASTA text:
+// a record starts at a line whose first byte is '>' or '@' (kseq.h:247,263); its name is the header up to the
+// first isspace byte (kseq.h:254), the rest of the header line is a comment; the sequence is the
+// concatenation of the following lines without their newlines, blank lines skipped (kseq.h:263-269).
+//
+// The sequence arena is therefore a pure stream compaction of the file: keep every byte that is neither a
+// newline nor part of a header line.  One pass, 16 KiB tiles staged by 1-D TMA:
+//   * newline mask by SWAR + dp4a; '>' '@' '+' '\r' are only tested where they matter (line starts / the byte
+//     before a newline), so there is a single full-width mask;
+//   * "am I inside a header line at the start of the tile" is a last-writer scan over tiles, resolved with a
+//     look-back: a tile that contains a newline knows its own carry-out and publishes it immediately;
+//   * kept-byte and record counts get their global offsets from two decoupled look-backs;
+//   * kept bytes are compacted in shared memory at the destination's 16-byte phase and stored with 128-bit writes.
+// Outputs: the arena, and per record its file position and its offset in the arena.  Names are cut out by two
+// tiny per-record kernels afterwards.
+//
+// Inputs this kernel does not take (the caller falls back to the host reader, raftgpu_load_fasta): FASTQ
+// ('+' at a line start), any '\r' before a newline (kseq's strip rule depends on the accumulated length,
+// kseq.h:189-190), a file that does not begin with '>' or '@', a marker as the very last byte.
+#include "kernels.h"
+
+namespace raftk {
+
+constexpr int F0_THREADS = 256;
+constexpr int F0_TILE = 16384;
+constexpr int F0_WORDS = F0_TILE / 32; // 512 mask words, two per thread
+
+struct __align__(16) F0Smem {
+    uint8_t  text[F0_TILE + 16];
+    uint8_t  out[F0_TILE + 32];
+    unsigned nl[F0_WORDS + 1];  // (+1: all-ones sentinel)
+    unsigned hdr[F0_WORDS];     // byte belongs to a header line (including its newline)
+    uint64_t bar;
+    uint64_t bcast[2];
+    int      scan_ws[34];
+    int      tile;
+    int      last_nl;           // position of the last newline in the tile, -1 if none
+    int      carry_in;
+};
+
+__device__ __forceinline__ unsigned f0_zero_flags(unsigned x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ unsigned f0_eq_mask16(const uint4& v, unsigned c4)
+{
+    unsigned lo = __dp4a(f0_zero_flags(v.x ^ c4), 0x08040201u, 0u);
+    lo = __dp4a(f0_zero_flags(v.y ^ c4), 0x80402010u, lo);
+    unsigned hi = __dp4a(f0_zero_flags(v.z ^ c4), 0x08040201u, 0u);
+    hi = __dp4a(f0_zero_flags(v.w ^ c4), 0x80402010u, hi);
+    return (lo >> 7) | ((hi >> 7) << 8);
+}
+__device__ __forceinline__ int f0_next_bit(const unsigned* m, int from)
+{ // first set bit at position >= from; the sentinel word makes it return >= F0_TILE when there is none
+    int      w = from >> 5;
+    unsigned x = m[w] & (0xFFFFFFFFu << (from & 31));
+    while (!x) x = m[++w];
+    return (w << 5) + __ffs(x) - 1;
+}
+
+// carry status word: bits 63..62 = 2 when resolved (value in bit 0); 0 = not yet published; 1 = transparent
+// (the tile has no newline: its carry-out equals its carry-in)
+constexpr uint64_t F0_RESOLVED = 2ull << 62, F0_TRANSPARENT = 1ull << 62;
+
+__device__ __forceinline__ int f0_resolve_carry(const uint64_t* status, int tile)
+{ // all lanes of one warp; nearest predecessor with a resolved value
+    int look = tile - 1;
+    while (look >= 0) {
+        int      idx = look - lane_id();
+        uint64_t w = F0_RESOLVED; // before the file: not in a header
+        if (idx >= 0) {
+            w = ld_relaxed_u64(status + idx);
+            while ((w >> 62) == 0) { __nanosleep(20); w = ld_relaxed_u64(status + idx); }
+        }
+        unsigned pm = __ballot_sync(FULL, (w >> 62) == 2);
+        if (pm) { int src = __ffs(pm) - 1; return (int)(__shfl_sync(FULL, (unsigned)(w & 1ull), src)); }
+        look -= 32;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a)
+{
+    extern __shared__ __align__(16) uint8_t f0_raw[];
+    F0Smem& s = *reinterpret_cast<F0Smem*>(f0_raw);
+    const int tid = threadIdx.x, lane = lane_id();
+    if (tid == 0) { s.tile = atomicAdd(a.ticket, 1); s.last_nl = -1; mbar_init(&s.bar, 1); }
+    __syncthreads();
+    const int     tile = s.tile;
+    const int64_t t0 = (int64_t)tile * F0_TILE;
+    const int64_t avail = a.nbytes - t0;
+    const int     want = (int)(avail < F0_TILE ? avail : F0_TILE);
+    const int     bulk = want & ~15;
+    if (tid == 0 && bulk > 0) { mbar_expect_tx(&s.bar, (uint32_t)bulk); tma_load_1d(s.text, a.text + t0, (uint32_t)bulk, &s.bar); }
+    for (int j = bulk + tid; j < F0_TILE + 16; j += F0_THREADS) s.text[j] = (j < want) ? a.text[t0 + j] : (uint8_t)'\n';
+    // the byte before the tile decides whether its first byte starts a line
+    const bool prev_nl = (t0 == 0) || a.text[t0 - 1] == '\n';
+    if (bulk > 0) mbar_wait(&s.bar, 0);
+    __syncthreads();
+
+    // ---- newline mask (bytes past the end of the file were filled with '\n': they are dropped like any newline)
+    const uint4* t16 = reinterpret_cast<const uint4*>(s.text);
+    int          my_last = -1;
+    for (int g = tid; g < F0_TILE / 16; g += F0_THREADS) {
+        unsigned m = f0_eq_mask16(t16[g], 0x0A0A0A0Au);
+        unsigned p = __shfl_down_sync(FULL, m, 1);
+        if (!(lane & 1)) s.nl[g >> 1] = m | (p << 16);
+        const int room = want - g * 16; // bytes of this group inside the file
+        const unsigned mv = room >= 16 ? m : (room > 0 ? (m & ((1u << room) - 1u)) : 0u);
+        if (mv) my_last = g * 16 + (31 - __clz(mv));
+    }
+    for (int w = tid; w < F0_WORDS; w += F0_THREADS) s.hdr[w] = 0;
+    if (tid == 0) s.nl[F0_WORDS] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_last = max(my_last, __shfl_xor_sync(FULL, my_last, d));
+    if (lane == 0 && my_last >= 0) atomicMax(&s.last_nl, my_last);
+    __syncthreads();
+
+    // ---- line starts in my two words: markers open header lines; '+' or a CR before a newline are not handled here
+    const int wlo = tid * 2;
+    unsigned  mk[2] = {0, 0};
+    int       flags = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int w = wlo + i;
+        unsigned  prev = w ? (s.nl[w - 1] >> 31) : (prev_nl ? 1u : 0u);
+        unsigned  ls = (s.nl[w] << 1) | prev; // byte p follows a newline (blank lines included: their byte is '\n', tested below)
+        unsigned  nlw = s.nl[w];
+        // a '\r' right before a newline
+        unsigned m = nlw;
+        while (m) {
+            int bit = __ffs(m) - 1; m &= m - 1;
+            int q = (w << 5) + bit;
+            if (q < want) { uint8_t b = q ? s.text[q - 1] : (t0 ? a.text[t0 - 1] : (uint8_t)0); if (b == '\r') flags |= 1; }
+        }
+        m = ls;
+        while (m) {
+            int bit = __ffs(m) - 1; m &= m - 1;
+            int p = (w << 5) + bit;
+            if (p >= want) break;
+            uint8_t c = s.text[p];
+            if (c == '>' || c == '@') {
+                mk[i] |= 1u << bit;
+                if (t0 + p == a.nbytes - 1) flags |= 8; // marker as the last byte of the file: kseq returns no record
+                // header line [p, e]: e = its newline (or the end of the tile)
+                int e = f0_next_bit(s.nl, p);
+                if (e >= F0_TILE) e = F0_TILE - 1;
+                int w0 = p >> 5, w1 = e >> 5;
+                for (int ww = w0; ww <= w1; ww++) {
+                    unsigned lo = ww == w0 ? (0xFFFFFFFFu << (p & 31)) : 0xFFFFFFFFu;
+                    unsigned hi = ww == w1 ? (0xFFFFFFFFu >> (31 - (e & 31))) : 0xFFFFFFFFu;
+                    atomicOr(&s.hdr[ww], lo & hi);
+                }
+            } else if (c == '+') flags |= 2;
+        }
+    }
+    if (t0 == 0 && tid == 0 && a.first_chunk && !(s.text[0] == '>' || s.text[0] == '@')) flags |= 4;
+    if (tid == 0 && a.last_chunk && t0 + want == a.nbytes && s.text[want - 1] == '\r') flags |= 1; // CR at EOF: kseq's strip rule again
+    if (flags) atomicOr(a.flags, flags);
+
+    // ---- carry: is the tile's first byte inside a header line?  (last-writer scan over tiles)
+    if (tid == 0) {
+        const int ql = s.last_nl;
+        uint64_t  st;
+        if (ql >= 0) { // the line open at the end of the tile starts at ql+1 (in this tile, or exactly at the next tile)
+            int p = ql + 1;
+            st = F0_RESOLVED | ((p < want && (s.text[p] == '>' || s.text[p] == '@')) ? 1ull : 0ull);
+        } else if (prev_nl) {
+            st = F0_RESOLVED | ((s.text[0] == '>' || s.text[0] == '@') ? 1ull : 0ull);
+        } else st = F0_TRANSPARENT;
+        st_relaxed_u64(a.st_carry + tile, st);
+    }
+    if (tid < 32) {
+        int cin = prev_nl ? 0 : f0_resolve_carry(a.st_carry, tile);
+        if (lane == 0) {
+            s.carry_in = cin;
+            if (s.last_nl < 0 && !prev_nl) st_relaxed_u64(a.st_carry + tile, F0_RESOLVED | (uint64_t)cin); // transparent tile: now known
+        }
+    }
+    __syncthreads();
+    if (s.carry_in && tid == 0) { // the header line continues from the previous tile up to the first newline
+        int e = f0_next_bit(s.nl, 0);
+        if (e >= F0_TILE) e = F0_TILE - 1;
+        for (int ww = 0; ww <= (e >> 5); ww++) atomicOr(&s.hdr[ww], ww == (e >> 5) ? (0xFFFFFFFFu >> (31 - (e & 31))) : 0xFFFFFFFFu);
+    }
+    __syncthreads();
+
+    // ---- keep = neither newline nor header; counts and global offsets
+    unsigned keep[2];
+    int      nkeep = 0, nmk = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { keep[i] = ~(s.nl[wlo + i] | s.hdr[wlo + i]); nkeep += __popc(keep[i]); nmk += __popc(mk[i]); }
+    int tot_keep, tot_mk;
+    int ex_keep = block_exclusive_sum<int, F0_THREADS>(nkeep, s.scan_ws, &tot_keep);
+    __syncthreads();
+    int ex_mk = block_exclusive_sum<int, F0_THREADS>(nmk, s.scan_ws, &tot_mk);
+    if (tid == 0) { lookback_publish(a.st_keep, tile, (uint64_t)tot_keep); lookback_publish(a.st_rec, tile, (uint64_t)tot_mk); }
+    const int64_t base_keep = (int64_t)lookback_wait(a.st_keep, tile, (uint64_t)tot_keep, &s.bcast[0]);
+    const int64_t base_rec = (int64_t)lookback_wait(a.st_rec, tile, (uint64_t)tot_mk, &s.bcast[1]);
+    if (tid == 0 && tile == a.n_tiles - 1) { a.totals[0] = base_rec + tot_mk; a.totals[1] = base_keep + tot_keep; }
+
+    // ---- records that start in my words
+    {
+        int kept_before = ex_keep, r = ex_mk;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            unsigned m = mk[i];
+            while (m) {
+                int     bit = __ffs(m) - 1; m &= m - 1;
+                int64_t idx = base_rec + r++;
+                if (idx < a.rec_cap) {
+                    a.rec_pos[idx] = t0 + ((wlo + i) << 5) + bit;
+                    a.seq_off[idx] = a.seq_off_base + base_keep + kept_before + __popc(keep[i] & ((1u << bit) - 1u)); // header bytes are not kept
+                }
+            }
+            kept_before += __popc(keep[i]);
+        }
+    }
+    // ---- compact the kept bytes at the destination's 16-byte phase, then aligned 128-bit stores
+    const uintptr_t gdst0 = (uintptr_t)a.seq_out + (uintptr_t)base_keep;
+    const int       phase = (int)(gdst0 & 15);
+    {
+        uint8_t* o = s.out + phase + ex_keep;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            unsigned       m = keep[i];
+            const uint8_t* src = s.text + ((wlo + i) << 5);
+            if (m == 0xFFFFFFFFu) { // whole word kept (the common case inside sequence lines)
+#pragma unroll
+                for (int k = 0; k < 32; k++) o[k] = src[k];
+                o += 32;
+            } else {
+                while (m) { int bit = __ffs(m) - 1; m &= m - 1; *o++ = src[bit]; }
+            }
+        }
+    }
+    __syncthreads();
+    const uintptr_t ga1 = gdst0 + (uintptr_t)tot_keep;
+    uintptr_t       fa = (gdst0 + 15) & ~(uintptr_t)15, la = ga1 & ~(uintptr_t)15;
+    if (fa > la) { fa = ga1; la = ga1; }
+    const uint8_t* sb = s.out + phase;
+    for (uintptr_t x = gdst0 + tid; x < fa; x += F0_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
+    for (uintptr_t x = fa + (uintptr_t)tid * 16; x < la; x += (uintptr_t)F0_THREADS * 16)
+        stg_stream(reinterpret_cast<uint4*>(x), *reinterpret_cast<const uint4*>(sb + (x - gdst0)));
+    for (uintptr_t x = la + tid; x < ga1; x += F0_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
+}
+
+int         fasta_tokenize_tiles(int64_t nbytes) { return (int)((nbytes + F0_TILE - 1) / F0_TILE); }
+cudaError_t launch_fasta_tokenize(const FastaTokArgs& a, cudaStream_t st)
+{
+    if (a.n_tiles <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_fasta_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(F0Smem));
+    if (e != cudaSuccess) return e;
+    k_fasta_tokenize<<<a.n_tiles, F0_THREADS, sizeof(F0Smem), st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- names: header up to the first isspace byte (kseq.h:254)
+__global__ void __launch_bounds__(256) k_fasta_name_len(const uint8_t* __restrict__ text, int64_t nbytes, const int64_t* __restrict__ rec_pos,
+                                                         int64_t n, int32_t* name_len)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t p = rec_pos[i] + 1, q = p;
+    while (q < nbytes) { uint8_t c = text[q]; if (c == ' ' || (c >= 9 && c <= 13)) break; q++; }
+    name_len[i] = (int32_t)(q - p);
+}
+__global__ void __launch_bounds__(256) k_fasta_name_copy(const uint8_t* __restrict__ text, const int64_t* __restrict__ rec_pos,
+                                                          const int64_t* __restrict__ name_off, int64_t n, uint8_t* names)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* src = text + rec_pos[i] + 1;
+    uint8_t*       dst = names + name_off[i];
+    int64_t        len = name_off[i + 1] - name_off[i];
+    for (int64_t k = 0; k < len; k++) dst[k] = src[k];
+}
+void launch_fasta_name_len(const uint8_t* text, int64_t nbytes, const int64_t* rec_pos, int64_t n, int32_t* name_len, cudaStream_t st)
+{
+    if (n > 0) k_fasta_name_len<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(text, nbytes, rec_pos, n, name_len);
+}
+void launch_fasta_name_copy(const uint8_t* text, const int64_t* rec_pos, const int64_t* name_off, int64_t n, uint8_t* names, cudaStream_t st)
+{
+    if (n > 0) k_fasta_name_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(text, rec_pos, name_off, n, names);
+}
+
+__global__ void __launch_bounds__(256) k_add_offset_i64(const int64_t* __restrict__ src, int64_t n, int64_t add, int64_t* dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+void launch_add_offset_i64(const int64_t* src, int64_t n, int64_t add, int64_t* dst, cudaStream_t st)
+{
+    if (n > 0) k_add_offset_i64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, n, add, dst);
+}
+
+} // namespace raftk

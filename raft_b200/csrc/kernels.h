@@ -21,6 +21,27 @@ struct ErrState {
 cudaError_t launch_name_build(NameTable* out_table_desc_host, void* slots, unsigned long long capacity, unsigned long long seed,
                               const uint8_t* names, const int64_t* name_off, int64_t n, ErrState* err, cudaStream_t st);
 
+// ---------------------------------------------------------------- K0 (k0_fasta.cu)
+struct FastaTokArgs {
+    const uint8_t* text;      // chunk of FASTA text starting at a line start, 16-byte aligned
+    int64_t        nbytes;
+    int            n_tiles, first_chunk, last_chunk;
+    uint8_t*       seq_out;   // arena position of this chunk's first kept byte
+    int64_t        seq_off_base; // arena offset of seq_out
+    int64_t*       rec_pos;   // chunk-relative position of each record's marker   (this chunk's records)
+    int64_t*       seq_off;   // arena offset of each record's first base
+    int64_t        rec_cap;
+    uint64_t *     st_carry, *st_keep, *st_rec; // n_tiles words each, zeroed
+    int*           ticket;    // zeroed
+    int*           flags;     // 1 CR before newline, 2 '+' line (FASTQ), 4 no leading marker, 8 marker is the last byte
+    long long*     totals;    // [0] records, [1] kept bytes of this chunk
+};
+int         fasta_tokenize_tiles(int64_t nbytes);
+cudaError_t launch_fasta_tokenize(const FastaTokArgs& a, cudaStream_t st);
+void launch_fasta_name_len(const uint8_t* text, int64_t nbytes, const int64_t* rec_pos, int64_t n, int32_t* name_len, cudaStream_t st);
+void launch_add_offset_i64(const int64_t* src, int64_t n, int64_t add, int64_t* dst, cudaStream_t st);
+void launch_fasta_name_copy(const uint8_t* text, const int64_t* rec_pos, const int64_t* name_off, int64_t n, uint8_t* names, cudaStream_t st);
+
 // ---------------------------------------------------------------- K1 (k1_paf.cu)
 struct PafTokArgs {
     const uint8_t* text;

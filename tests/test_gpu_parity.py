@@ -301,3 +301,73 @@ def test_deferred_sequence_upload(pinned):
         assert ctx.fetch(api.OUT_COVERAGE) == ref.cov_txt
         assert ctx.digest(api.OUT_READS_FASTA) == O.digest(ref.fasta)
     ctx.close()
+
+
+def _fasta_variants():
+    rng = np.random.default_rng(7)
+    seqs = [bytes(rng.choice(list(b"ACGTN"), int(L)).astype(np.uint8)) for L in (1, 59, 60, 61, 0, 16384, 16385, 40000, 7, 100000, 3, 0, 250)]
+    names = [b"r%d" % i for i in range(len(seqs))]
+    def build(width, comment=b"", marker=b">", trailing=True, blank=False):
+        out = []
+        for i, (nm, sq) in enumerate(zip(names, seqs)):
+            hdr = (b"@" if (marker == b"mix" and i % 3 == 0) else b">") + nm + ((b" " + comment + b"\t x=%d" % i) if comment else b"") + b"\n"
+            body = b"\n".join(sq[k:k + width] for k in range(0, len(sq), width)) if width else sq
+            out.append(hdr + body + (b"\n" if (body or not blank) else b"") + (b"\n\n" if blank and i % 2 else b""))
+        txt = b"".join(out)
+        return txt if trailing else txt.rstrip(b"\n")
+    long_comment = b"c" * 20000  # header lines longer than a 16 KiB tile
+    return {"wrap60": build(60), "wrap61c": build(61, b"some comment"), "unwrapped": build(0), "wrap80_noeol": build(80, trailing=False),
+            "mixmarkers": build(70, marker=b"mix"), "blank_lines": build(75, blank=True), "huge_header": build(100, long_comment),
+            "wrap1": build(1)}
+
+
+@pytest.mark.parametrize("name", sorted(_fasta_variants()))
+def test_device_fasta_ingest_matches_kseq_grammar(name):
+    """Row f2: the device FASTA tokenizer yields the records of loadFASTA/kseq_read (oracle restatement, pinned by golden)."""
+    text = _fasta_variants()[name]
+    ref = O.parse_fasta(text)
+    p = api.AlgoParams(est_cov=3)
+    paf = b"".join(b"\t".join([b"r3", b"61", b"0", b"61", b"+", b"r%d" % j, b"1", b"0", b"1", b"1", b"1", b"9"]) + b"\n" for j in (5, 7))
+    want = O.run(ref, paf, O.make_params(est_cov=3))
+    assert want.status == 0
+    for chunks in (None, [5, 1000, 16384, 1, len(text)]):
+        ctx = api.Context(p)
+        buf = np.frombuffer(text, np.uint8)
+        if chunks is None:
+            ctx.ingest_fasta(buf, len(text), last=True, total_hint=len(text))
+        else:
+            pos = 0
+            for k, c in enumerate(chunks):
+                piece = buf[pos:pos + c]
+                ctx.ingest_fasta(np.ascontiguousarray(piece), len(piece), last=(k == len(chunks) - 1))
+                pos += len(piece)
+        ctx.ingest_paf(np.frombuffer(paf, np.uint8), len(paf), last=True)
+        st = ctx.run()
+        assert st.n_reads == ref.n
+        np.testing.assert_array_equal(ctx.table(api.TAB_BIN_OFF), want.bin_off)
+        assert ctx.fetch(api.OUT_READS_FASTA) == want.fasta     # names, lengths and every base in place
+        assert ctx.fetch(api.OUT_COVERAGE) == want.cov_txt
+        ctx.close()
+
+
+def test_device_fasta_ingest_rejects_what_it_does_not_take():
+    p = api.AlgoParams(est_cov=3)
+    for text in (b"@a\nACGT\n+\nIIII\n", b">a\r\nACGT\r\n", b"junk\n>a\nAC\n", b">a\nAC\n>"):
+        ctx = api.Context(p)
+        with pytest.raises(api.RaftError) as ei:
+            ctx.ingest_fasta(np.frombuffer(text, np.uint8), len(text), last=True)
+        assert ei.value.status == -12
+        ctx.close()
+
+
+def test_device_fasta_ingest_full_pipeline():
+    ds = synth.make_dataset("C1", 0.1, True, seed=77)
+    p = api.AlgoParams.from_args(ds.args)
+    text = synth.format_fasta(ds.reads, wrap=70)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    ctx = api.Context(p)
+    ctx.ingest_fasta(np.frombuffer(text, np.uint8), len(text), last=True, total_hint=len(text))
+    ctx.ingest_paf(np.frombuffer(ds.paf, np.uint8), len(ds.paf), last=True)
+    st = ctx.run()
+    compare_all(ctx, st, ref)
+    ctx.close()
