@@ -26,6 +26,8 @@ namespace raftk {
 constexpr int F0_THREADS = 256;
 constexpr int F0_TILE = 16384;
 constexpr int F0_WORDS = F0_TILE / 32; // 512 mask words, two per thread
+constexpr int F0_RUNCAP = 1024;        // run pieces listed per tile (more: byte-wise path)
+constexpr int F0_PIECE = 1024;
 
 struct __align__(16) F0Smem {
     uint8_t  text[F0_TILE + 16];
@@ -38,6 +40,9 @@ struct __align__(16) F0Smem {
     int      tile;
     int      last_nl;           // position of the last newline in the tile, -1 if none
     int      carry_in;
+    int      n_runs;
+    unsigned drop_sum[F0_WORDS / 32]; // bit j of word k: mask word 32k+j has a dropped byte
+    uint16_t run_src[F0_RUNCAP], run_dst[F0_RUNCAP], run_len[F0_RUNCAP]; // kept runs, cut into pieces of <= 1 KiB
 };
 
 __device__ __forceinline__ unsigned f0_zero_flags(unsigned x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
@@ -215,22 +220,72 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
             kept_before += __popc(keep[i]);
         }
     }
-    // ---- compact the kept bytes at the destination's 16-byte phase, then aligned 128-bit stores
+    // ---- compact the kept bytes at the destination's 16-byte phase, then aligned 128-bit stores.
+    // Kept bytes come in long runs (whole lines): list the runs (pieces of <= 1 KiB) and let each warp copy pieces with
+    // lane-consecutive bytes; per-thread copying of its own 64 bytes would be a 16-way shared-memory bank conflict.
     const uintptr_t gdst0 = (uintptr_t)a.seq_out + (uintptr_t)base_keep;
     const int       phase = (int)(gdst0 & 15);
+    if (tid == 0) s.n_runs = 0;
+    // summary of the dropped-byte mask (one ballot per 32 words) so that the end of a long run is found in a few steps
+    for (int w = tid; w < F0_WORDS; w += F0_THREADS) {
+        unsigned any = __ballot_sync(FULL, (s.nl[w] | s.hdr[w]) != 0);
+        if (lane == 0) s.drop_sum[w >> 5] = any;
+    }
+    __syncthreads();
     {
+        int dst = ex_keep;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int      w = wlo + i;
+            const unsigned k = keep[i];
+            const unsigned prevbit = w ? ((~(s.nl[w - 1] | s.hdr[w - 1])) >> 31) : 0u; // was the byte before this word kept?
+            unsigned       starts = k & ~((k << 1) | prevbit);
+            while (starts) {
+                int bit = __ffs(starts) - 1; starts &= starts - 1;
+                int p = (w << 5) + bit;
+                // run end: first dropped byte at or after p
+                int      ww = w;
+                unsigned d = (s.nl[ww] | s.hdr[ww]) & (0xFFFFFFFFu << bit); // dropped bits at or after p in this word
+                if (!d) { // next mask word with a dropped byte, through the summary
+                    int      sw = (w + 1) >> 5;
+                    unsigned sm = sw < F0_WORDS / 32 ? (s.drop_sum[sw] & (0xFFFFFFFFu << ((w + 1) & 31))) : 0u;
+                    if (((w + 1) & 31) == 0 && sw < F0_WORDS / 32) sm = s.drop_sum[sw];
+                    while (!sm && ++sw < F0_WORDS / 32) sm = s.drop_sum[sw];
+                    if (sm) { ww = (sw << 5) + __ffs(sm) - 1; d = s.nl[ww] | s.hdr[ww]; }
+                }
+                int e = d ? (ww << 5) + __ffs(d) - 1 : F0_TILE;
+                int len = e - p, dd = dst + __popc(k & ((1u << bit) - 1u));
+                for (int o = 0; o < len; o += F0_PIECE) {
+                    int slot = atomicAdd(&s.n_runs, 1);
+                    if (slot < F0_RUNCAP) { s.run_src[slot] = (uint16_t)(p + o); s.run_dst[slot] = (uint16_t)(dd + o); s.run_len[slot] = (uint16_t)min(F0_PIECE, len - o); }
+                }
+            }
+            dst += __popc(k);
+        }
+    }
+    __syncthreads();
+    if (s.n_runs <= F0_RUNCAP) {
+        const int nr = s.n_runs, warp = warp_id();
+        for (int r = warp; r < nr; r += F0_THREADS / 32) {
+            const uint8_t* src = s.text + s.run_src[r];
+            uint8_t*       o = s.out + phase + s.run_dst[r];
+            const int      n = s.run_len[r];
+            // realigning copy: bytes up to the first 16-byte boundary of the destination, 16-byte chunks, bytes
+            int head = (int)((16 - (smem_u32(o) & 15)) & 15);
+            if (head > n) head = n;
+            if (lane < head) o[lane] = src[lane];
+            const int nbody = (n - head) >> 4;
+            for (int c = lane; c < nbody; c += 32) *reinterpret_cast<uint4*>(o + head + (c << 4)) = lds_unaligned16(src + head + (c << 4));
+            const int done = head + (nbody << 4);
+            if (done + lane < n) o[done + lane] = src[done + lane];
+        }
+    } else { // pathological tile (thousands of tiny lines): every thread copies the kept bytes of its own words
         uint8_t* o = s.out + phase + ex_keep;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             unsigned       m = keep[i];
             const uint8_t* src = s.text + ((wlo + i) << 5);
-            if (m == 0xFFFFFFFFu) { // whole word kept (the common case inside sequence lines)
-#pragma unroll
-                for (int k = 0; k < 32; k++) o[k] = src[k];
-                o += 32;
-            } else {
-                while (m) { int bit = __ffs(m) - 1; m &= m - 1; *o++ = src[bit]; }
-            }
+            while (m) { int bit = __ffs(m) - 1; m &= m - 1; *o++ = src[bit]; }
         }
     }
     __syncthreads();

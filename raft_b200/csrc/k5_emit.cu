@@ -277,36 +277,6 @@ struct __align__(16) FeSmem {
     uint64_t  full[FE_SLOTS], empty[FE_SLOTS];
 };
 
-__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t* sp)
-{
-    const unsigned sa = (unsigned)(smem_u32(sp) & 15u);
-    const uint4*   b = reinterpret_cast<const uint4*>(sp - sa);
-    uint4          q0 = b[0];
-    if (sa == 0) return q0;
-    uint4          q1 = b[1];
-    const unsigned bs = (sa & 3u) * 8u;
-    uint4          o;
-    switch (sa >> 2) {
-    case 0:
-        o.x = __funnelshift_r(q0.x, q0.y, bs); o.y = __funnelshift_r(q0.y, q0.z, bs);
-        o.z = __funnelshift_r(q0.z, q0.w, bs); o.w = __funnelshift_r(q0.w, q1.x, bs);
-        break;
-    case 1:
-        o.x = __funnelshift_r(q0.y, q0.z, bs); o.y = __funnelshift_r(q0.z, q0.w, bs);
-        o.z = __funnelshift_r(q0.w, q1.x, bs); o.w = __funnelshift_r(q1.x, q1.y, bs);
-        break;
-    case 2:
-        o.x = __funnelshift_r(q0.z, q0.w, bs); o.y = __funnelshift_r(q0.w, q1.x, bs);
-        o.z = __funnelshift_r(q1.x, q1.y, bs); o.w = __funnelshift_r(q1.y, q1.z, bs);
-        break;
-    default:
-        o.x = __funnelshift_r(q0.w, q1.x, bs); o.y = __funnelshift_r(q1.x, q1.y, bs);
-        o.z = __funnelshift_r(q1.y, q1.z, bs); o.w = __funnelshift_r(q1.z, q1.w, bs);
-        break;
-    }
-    return o;
-}
-
 // consumer threads (index ct of FE_CONSUMERS): n bytes from shared memory (any alignment) to global (any alignment)
 __device__ __forceinline__ void consumers_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n, int ct)
 {

@@ -62,6 +62,34 @@ __global__ void k_seq(uint8_t* seq, const int64_t* __restrict__ seq_off, const i
     else for (int k = 0; k < cnt; k++) seq[x0 + k] = (uint8_t)(w[k >> 2] >> ((k & 3) * 8));
 }
 
+// unwrapped FASTA text of reads [r0, r0+n): ">" name(36) "\n" bases "\n"; one thread per 16 output bytes
+__global__ void k_fasta_text(uint8_t* text, const int64_t* __restrict__ seq_off, const int64_t* __restrict__ start,
+                             const int8_t* __restrict__ strand, int64_t r0, int64_t n, int64_t total, uint64_t seed)
+{
+    int64_t x0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x0 >= total) return;
+    const int64_t base = seq_off[r0] + 39 * r0;        // text offset of record r0 in the whole file
+    auto rec_off = [&](int64_t i) { return seq_off[i] + 39 * i - base; };
+    int64_t lo = r0, hi = r0 + n;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rec_off(mid) <= x0) lo = mid; else hi = mid; }
+    int64_t r = lo, ro = rec_off(r), L = seq_off[r + 1] - seq_off[r];
+    for (int k = 0; k < 16 && x0 + k < total; k++) {
+        int64_t x = x0 + k;
+        while (x >= ro + 39 + L) { r++; ro = rec_off(r); L = seq_off[r + 1] - seq_off[r]; }
+        int64_t off = x - ro;
+        uint8_t b;
+        if (off == 0) b = '>';
+        else if (off <= 36) b = name_char(seed, r, (int)off - 1);
+        else if (off == 37 || off == 38 + L) b = '\n';
+        else {
+            int64_t q = off - 38;
+            if (strand[r]) { uint8_t g = genome_base(seed, start[r] + (L - 1 - q)); b = g == 'A' ? 'T' : g == 'C' ? 'G' : g == 'G' ? 'C' : 'A'; }
+            else b = genome_base(seed, start[r] + q);
+        }
+        text[x] = b;
+    }
+}
+
 struct PafCols {
     const int64_t *q, *t, *qs, *qe, *ts, *te;
     const int8_t*  rev;
@@ -116,6 +144,15 @@ int synth_seq(void* seq, const void* seq_off, const void* start, const void* str
     if (thr > 0)
         k_seq<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint8_t*)seq, (const int64_t*)seq_off, (const int64_t*)start,
                                                                                    (const int8_t*)strand, n, total, seed);
+    return (int)cudaGetLastError();
+}
+int synth_fasta_text(void* text, const void* seq_off, const void* start, const void* strand, int64_t r0, int64_t n, int64_t total, uint64_t seed,
+                     void* stream)
+{
+    int64_t thr = (total + 15) / 16;
+    if (thr > 0)
+        k_fasta_text<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint8_t*)text, (const int64_t*)seq_off, (const int64_t*)start,
+                                                                                          (const int8_t*)strand, r0, n, total, seed);
     return (int)cudaGetLastError();
 }
 int synth_paf_sizes(const void* q, const void* t, const void* qs, const void* qe, const void* ts, const void* te, const void* rev,

@@ -23,6 +23,7 @@ def _lib():
         vp, i64, u64 = C.c_void_p, C.c_int64, C.c_uint64
         L.synth_names.argtypes = [vp, i64, u64, vp]
         L.synth_seq.argtypes = [vp, vp, vp, vp, i64, i64, u64, vp]
+        L.synth_fasta_text.argtypes = [vp, vp, vp, vp, i64, i64, i64, u64, vp]
         L.synth_paf_sizes.argtypes = [vp] * 8 + [i64, u64, vp, vp]
         L.synth_paf_write.argtypes = [vp] * 8 + [i64, u64, vp, vp, vp]
         _LIB = L
@@ -202,3 +203,13 @@ def gen_seq(ds, r0, r1):
     L.synth_seq(seq.data_ptr(), off.data_ptr(), ds.start[r0:r1].contiguous().data_ptr(), ds.strand[r0:r1].contiguous().data_ptr(),
                 r1 - r0, total, ds.seed, _stream())
     return seq
+
+
+def gen_fasta_text(ds, r0, r1, out=None):
+    """Unwrapped FASTA text (">" name "\\n" bases "\\n") of reads [r0, r1) as a uint8 device tensor."""
+    L = _lib()
+    total = int(ds.seq_off[r1] - ds.seq_off[r0]) + 39 * (r1 - r0)
+    if out is None or out.numel() < total:
+        out = torch.empty(total + 64, dtype=torch.uint8, device=ds.seq_off.device)
+    L.synth_fasta_text(out.data_ptr(), ds.seq_off.data_ptr(), ds.start.data_ptr(), ds.strand.data_ptr(), r0, r1 - r0, total, ds.seed, _stream())
+    return out, total
