@@ -9,7 +9,7 @@ CU        := nametable k0_fasta k1_paf k2_coverage k3_repeat_cut k5_emit api
 OBJS      := $(addprefix $(OBJ)/,$(addsuffix .o,$(CU))) $(OBJ)/host_io.o
 LIB       := raft_b200/libraft_b200.so
 
-all: $(LIB) raft_b200/raft raft_b200/libraft_synth.so oracle
+all: $(LIB) raft_b200/raft raft_b200/split_naive raft_b200/libraft_synth.so oracle
 
 $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh $(SRC)/coverage.cuh $(SRC)/covtext.cuh include/raft_b200.h
 	@mkdir -p $(OBJ)
@@ -28,10 +28,13 @@ raft_b200/libraft_synth.so: $(SRC)/synth_gen.cu $(SRC)/common.cuh
 raft_b200/raft: $(SRC)/raft_main.cpp $(LIB)
 	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -Lraft_b200 -lraft_b200 -Wl,-rpath,'$$ORIGIN'
 
+raft_b200/split_naive: $(SRC)/split_naive_main.cpp $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall $< -o $@ -Lraft_b200 -lraft_b200 -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(OBJ) $(LIB) raft_b200/raft raft_b200/libraft_synth.so
+	rm -rf $(OBJ) $(LIB) raft_b200/raft raft_b200/split_naive raft_b200/libraft_synth.so
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

@@ -55,7 +55,8 @@ typedef enum {
 } raftgpu_status;
 
 /* Output streams (files the reference writes: chop.hpp:333, repeat.hpp:85-87). */
-enum { RAFTGPU_OUT_COVERAGE = 0, RAFTGPU_OUT_LONG_REPEATS = 1, RAFTGPU_OUT_BED = 2, RAFTGPU_OUT_READS_FASTA = 3 };
+enum { RAFTGPU_OUT_COVERAGE = 0, RAFTGPU_OUT_LONG_REPEATS = 1, RAFTGPU_OUT_BED = 2, RAFTGPU_OUT_READS_FASTA = 3,
+       RAFTGPU_OUT_SPLIT_NAIVE = 4 /* only after raftgpu_split_naive */ };
 
 /* Integer tables for tests / downstream tools (raftgpu_fetch_table). */
 enum {
@@ -158,6 +159,12 @@ int raftgpu_digest(raftgpu_ctx *ctx, int which, uint64_t *digest);
 /* Copies an integer table to dst [host|device]; *n_elems receives the element count (call with
  * dst=NULL to size). */
 int raftgpu_fetch_table(raftgpu_ctx *ctx, int table, void *dst, size_t cap_bytes, size_t *n_elems);
+
+/* ---- split_naive (split_naive.cpp:10-44): every read cut into consecutive, non-overlapping pieces of
+ * `subread_length` bases, records ">" name "_" k "\n" bases "\n" (k from 1; an empty read gives no record).  Needs reads
+ * with sequence bytes (raftgpu_set_reads / raftgpu_ingest_fasta); independent of the PAF.  The bytes are then available
+ * as stream RAFTGPU_OUT_SPLIT_NAIVE through raftgpu_output_size / raftgpu_fetch / raftgpu_digest (same gather kernel). */
+int raftgpu_split_naive(raftgpu_ctx *ctx, int32_t subread_length);
 
 /* ---- multi-GPU (one context per rank; the exchange itself is done by the caller, e.g. NCCL
  * all-to-all over NVLink).  Reads are partitioned into contiguous id ranges; every rank holds all

@@ -68,6 +68,8 @@ def lib():
         _lib.orc_parse_fasta.restype = C.c_int64
         _lib.orc_parse_fasta.argtypes = [C.c_void_p, C.c_int64, C.POINTER(OrcFasta)]
         _lib.orc_free_fasta.argtypes = [C.POINTER(OrcFasta)]
+        _lib.orc_split_naive.restype = C.c_int64
+        _lib.orc_split_naive.argtypes = [C.POINTER(OrcReads), C.c_int32, C.POINTER(_P8)]
         _lib.orc_digest.restype = C.c_uint64
         _lib.orc_digest.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
     return _lib
@@ -159,6 +161,28 @@ def parse_fasta(text: bytes) -> Reads:
     names = _arr(f.names, int(name_off[-1]), np.uint8)
     L.orc_free_fasta(C.byref(f))
     return Reads(seq_off, seq, name_off, names)
+
+
+REF_SPLIT_BIN = os.path.join(HERE, "_ref", "split_naive")
+
+
+def split_naive(reads, sublen: int) -> bytes:
+    L = lib()
+    seq_off = np.ascontiguousarray(reads.seq_off, dtype=np.int64)
+    name_off = np.ascontiguousarray(reads.name_off, dtype=np.int64)
+    seq = np.ascontiguousarray(reads.seq, dtype=np.uint8)
+    names = np.ascontiguousarray(reads.names, dtype=np.uint8)
+    rd = OrcReads(len(seq_off) - 1, seq_off.ctypes.data, seq.ctypes.data if seq.size else None, name_off.ctypes.data,
+                  names.ctypes.data if names.size else None)
+    out = _P8()
+    n = L.orc_split_naive(C.byref(rd), sublen, C.byref(out))
+    if n < 0:
+        raise RuntimeError(f"orc_split_naive: {n}")
+    data = _bytes(out, n)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(out, C.c_void_p))
+    return data
 
 
 def digest(data: bytes, abs_offset=0) -> int:

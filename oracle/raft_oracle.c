@@ -553,3 +553,24 @@ void orc_free_fasta(orc_fasta_t *f)
     free(f->seq_off); free(f->seq); free(f->name_off); free(f->names);
     memset(f, 0, sizeof *f);
 }
+
+/* ------------------------------------------------------------------ split_naive (split_naive.cpp:22-37) */
+int64_t orc_split_naive(const orc_reads_t *rd, int32_t sublen, uint8_t **out)
+{
+    buf_t b = {0};
+    if (sublen < 1) return ORC_E_PARAM;
+    for (int64_t i = 0; i < rd->n_reads; i++) {
+        int64_t L = rd->seq_off[i + 1] - rd->seq_off[i];
+        int64_t k = 1;
+        for (int64_t a = 0; a < L; a += sublen, k++) { /* split_naive.cpp:27-29 */
+            int64_t n = a + sublen < L ? sublen : L - a;
+            buf_str(&b, ">"); buf_put(&b, rd->names + rd->name_off[i], rd->name_off[i + 1] - rd->name_off[i]);
+            buf_str(&b, "_"); buf_int(&b, k); buf_str(&b, "\n");          /* split_naive.cpp:32 */
+            buf_put(&b, rd->seq + rd->seq_off[i] + a, n); buf_str(&b, "\n");
+        }
+    }
+    if (b.oom) { free(b.p); return ORC_E_NOMEM; }
+    if (!b.p) b.p = (uint8_t *)calloc(1, 1);
+    *out = b.p;
+    return b.len;
+}

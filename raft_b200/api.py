@@ -12,6 +12,7 @@ import numpy as np
 from . import _lib
 
 OUT_COVERAGE, OUT_LONG_REPEATS, OUT_BED, OUT_READS_FASTA = 0, 1, 2, 3
+OUT_SPLIT_NAIVE = 4
 OPT_DEFER_SEQ_UPLOAD = 1
 OUT_SUFFIX = {OUT_COVERAGE: "coverage.txt", OUT_LONG_REPEATS: "long_repeats.txt", OUT_BED: "long_repeats.bed",
               OUT_READS_FASTA: "reads.fasta"}
@@ -127,6 +128,10 @@ class Context:
         self._keep = [lengths, name_off, names, own_seq_off, own_seq]
         self._ck(self.L.raftgpu_set_reads_sharded(self._h, n, _ptr(lengths), _ptr(name_off), _ptr(names), own_first,
                                                   own_count, _ptr(own_seq_off), _ptr(own_seq)))
+
+    def split_naive(self, subread_length: int):
+        """split_naive.cpp:10-44 on the device; bytes through fetch(OUT_SPLIT_NAIVE)."""
+        self._ck(self.L.raftgpu_split_naive(self._h, subread_length))
 
     # ---- a1/a2 create_pileup (chop.hpp:133-191)
     def ingest_paf(self, text, nbytes=None, last=True):

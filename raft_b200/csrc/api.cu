@@ -116,6 +116,12 @@ struct raftgpu_ctx {
     bool        emit_pending = false;
     int         emit_pending_which = 0;
 
+    // split_naive stream (raftgpu_split_naive)
+    int      sn_len = 0;
+    int64_t  sn_G = 0;
+    uint64_t sn_bytes = 0;
+    DevBuf   b_sn_cnt, b_sn_base, b_sn_read, b_sn_a, b_sn_b, b_sn_size, b_sn_off, b_sn_desc, b_sn_tile;
+
     // device FASTA ingest (raftgpu_ingest_fasta)
     bool    fasta_active = false;
     int64_t fa_n = 0, fa_bases = 0, fa_name_bytes = 0, fa_rec_cap = 0;
@@ -251,6 +257,7 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
     ctx->q_scattered = false; ctx->h_sym = 0;
     ctx->fasta_active = false; ctx->fa_n = ctx->fa_bases = ctx->fa_name_bytes = 0; ctx->fa_carry.clear();
+    ctx->sn_len = 0; ctx->sn_G = 0; ctx->sn_bytes = 0;
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
     ctx->emit_pending = false;
@@ -1069,8 +1076,8 @@ static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint
     cudaEventRecord(ctx->ev_emit[0], st);
     int rc = emit_window_impl(ctx, which, w0, w1, d, st);
     cudaEventRecord(ctx->ev_emit[1], st);
-    ctx->emit_pending = true; ctx->emit_pending_which = which;
-    ctx->stats.emit_launches[which]++; ctx->stats.emit_bytes[which] += (uint64_t)(w1 - w0);
+    ctx->emit_pending = true; ctx->emit_pending_which = which > 3 ? 3 : which; // the split_naive stream is accounted with the gather kernel
+    ctx->stats.emit_launches[which > 3 ? 3 : which]++; ctx->stats.emit_bytes[which > 3 ? 3 : which] += (uint64_t)(w1 - w0);
     return rc;
 }
 static void flush_emit_timer(raftgpu_ctx* ctx)
@@ -1107,6 +1114,17 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         ra.line_off = ctx->b_rep_line_off.as<int64_t>(); ra.m = m; ra.own_first = ctx->own_first; ra.dst = d; ra.w0 = w0; ra.w1 = w1;
         ra.read_first = r0; ra.read_last = std::min<int64_t>(r1, m);
         launch_rep_emit(ra, st);
+        CKL();
+    } else if (which == RAFTGPU_OUT_SPLIT_NAIVE) {
+        int rc = wait_seq_bytes(ctx, (int64_t)ctx->seq_host_bytes, st); // needs the whole arena (no output->arena map kept for this stream)
+        if (rc) return rc;
+        FastaEmitArgs fa{};
+        fa.desc = ctx->b_sn_desc.as<FragDesc>(); fa.G = ctx->sn_G; fa.seq = ctx->d_seq; fa.seq_off = ctx->d_seq_off;
+        fa.names = ctx->d_names; fa.name_off = ctx->d_name_off; fa.own_first = ctx->own_first; fa.read_num_base = 0;
+        fa.dst = d; fa.w0 = w0; fa.w1 = w1; fa.tile_frag = ctx->b_sn_tile.as<int32_t>();
+        fa.seq_safe_end = (ctx->d_seq == ctx->b_seq.as<uint8_t>()) ? ((ctx->total_read_len + 31) & ~(int64_t)15) : (ctx->total_read_len & ~(int64_t)15);
+        fa.sim = nullptr; fa.split_len = ctx->sn_len;
+        launch_fasta_emit(fa, st);
         CKL();
     } else if (which == RAFTGPU_OUT_BED) {
         if (ctx->real_reads) return RAFTGPU_OK;
@@ -1147,6 +1165,44 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
     return RAFTGPU_OK;
 }
 
+extern "C" int raftgpu_split_naive(raftgpu_ctx* ctx, int32_t sublen)
+{
+    if (!ctx || sublen < 1) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads || !ctx->have_seq) FAIL(RAFTGPU_E_STATE, "raftgpu_split_naive: set reads (with sequence bytes) first");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t m = ctx->m;
+    Misc*         M = ctx->misc();
+    CK(ctx->b_sn_cnt.ensure(sizeof(int32_t) * (size_t)(m + 1))); CK(ctx->b_sn_base.ensure(sizeof(int64_t) * (size_t)(m + 1)));
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_small(m) + 8)));
+    launch_split_counts(ctx->d_seq_off, m, sublen, ctx->b_sn_cnt.as<int32_t>(), ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_sn_cnt.as<int32_t>(), ctx->b_sn_base.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    long long G = 0;
+    CK(cudaMemcpyAsync(&G, ctx->b_sn_base.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx->b_sn_read.ensure(4 * (size_t)(G + 1))); CK(ctx->b_sn_a.ensure(4 * (size_t)(G + 1))); CK(ctx->b_sn_b.ensure(4 * (size_t)(G + 1)));
+    CK(ctx->b_sn_size.ensure(4 * (size_t)(G + 1))); CK(ctx->b_sn_off.ensure(8 * (size_t)(G + 1))); CK(ctx->b_sn_desc.ensure(sizeof(FragDesc) * (size_t)(G + 1)));
+    CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_small(G) + 8)));
+    launch_split_expand(ctx->d_seq_off, ctx->d_name_off, ctx->own_first, m, sublen, ctx->b_sn_base.as<int64_t>(), ctx->b_sn_read.as<int32_t>(),
+                        ctx->b_sn_a.as<int32_t>(), ctx->b_sn_b.as<int32_t>(), ctx->b_sn_size.as<int32_t>(), ctx->st);
+    CKL();
+    launch_scan_i32_to_i64(ctx->b_sn_size.as<int32_t>(), ctx->b_sn_off.as<int64_t>(), G, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
+    CKL();
+    long long bytes = 0;
+    CK(cudaMemcpyAsync(&bytes, ctx->b_sn_off.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx->b_sn_tile.ensure(sizeof(int32_t) * (size_t)(bytes / FASTA_TILE + 2)));
+    launch_fasta_tile_index(ctx->b_sn_off.as<int64_t>(), G, ctx->b_sn_tile.as<int32_t>(), ctx->st);
+    CKL();
+    launch_frag_desc(ctx->b_sn_read.as<int32_t>(), ctx->b_sn_a.as<int32_t>(), ctx->b_sn_b.as<int32_t>(), ctx->b_sn_size.as<int32_t>(),
+                     ctx->b_sn_off.as<int64_t>(), ctx->d_seq_off, G, ctx->b_sn_desc.as<FragDesc>(), ctx->st);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->sn_len = sublen; ctx->sn_G = G; ctx->sn_bytes = (uint64_t)bytes;
+    return RAFTGPU_OK;
+}
+
 extern "C" int raftgpu_set_option(raftgpu_ctx* ctx, int option, int64_t value)
 {
     if (!ctx) return RAFTGPU_E_ARG;
@@ -1165,7 +1221,12 @@ extern "C" int raftgpu_get_stats(raftgpu_ctx* ctx, raftgpu_stats* out)
 
 extern "C" int raftgpu_output_size(raftgpu_ctx* ctx, int which, uint64_t* nbytes)
 {
-    if (!ctx || !nbytes || which < 0 || which > 3) return RAFTGPU_E_ARG;
+    if (!ctx || !nbytes || which < 0 || which > 4) return RAFTGPU_E_ARG;
+    if (which == RAFTGPU_OUT_SPLIT_NAIVE) {
+        if (!ctx->sn_len) FAIL(RAFTGPU_E_STATE, "call raftgpu_split_naive first");
+        *nbytes = ctx->sn_bytes;
+        return RAFTGPU_OK;
+    }
     int st = layout_outputs(ctx);
     if (st) return st;
     *nbytes = ctx->stats.out_bytes[which];
@@ -1174,10 +1235,11 @@ extern "C" int raftgpu_output_size(raftgpu_ctx* ctx, int which, uint64_t* nbytes
 
 extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t* dst, size_t n)
 {
-    if (!ctx || which < 0 || which > 3 || (!dst && n)) return RAFTGPU_E_ARG;
-    int st = layout_outputs(ctx);
-    if (st) return st;
-    if (off > ctx->stats.out_bytes[which] || n > ctx->stats.out_bytes[which] - off) return RAFTGPU_E_ARG;
+    if (!ctx || which < 0 || which > 4 || (!dst && n)) return RAFTGPU_E_ARG;
+    int st = RAFTGPU_OK;
+    uint64_t stream_bytes = 0;
+    if ((st = raftgpu_output_size(ctx, which, &stream_bytes))) return st;
+    if (off > stream_bytes || n > stream_bytes - off) return RAFTGPU_E_ARG;
     if (!n) return RAFTGPU_OK;
     CK(cudaSetDevice(ctx->device));
     if (is_device_ptr(dst)) {
@@ -1207,11 +1269,11 @@ extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t*
 
 extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest)
 {
-    if (!ctx || !digest || which < 0 || which > 3) return RAFTGPU_E_ARG;
-    int st = layout_outputs(ctx);
+    if (!ctx || !digest || which < 0 || which > 4) return RAFTGPU_E_ARG;
+    uint64_t total = 0;
+    int st = raftgpu_output_size(ctx, which, &total);
     if (st) return st;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t total = ctx->stats.out_bytes[which];
     const size_t   W = (size_t)std::min<uint64_t>(WINDOW_BYTES, std::max<uint64_t>(total, 1));
     CK(ctx->b_stage[0].ensure(W + 64));
     CK(cudaMemsetAsync(&ctx->misc()->digest, 0, sizeof(unsigned long long), ctx->st));

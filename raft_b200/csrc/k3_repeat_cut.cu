@@ -211,6 +211,39 @@ void launch_frag_expand(const FragExpandArgs& a, cudaStream_t st)
     if (a.m > 0) k_frag_expand<<<(unsigned)((a.m + 255) / 256), 256, 0, st>>>(a);
 }
 
+// ---------------------------------------------------------------- split_naive
+__global__ void __launch_bounds__(256) k_split_counts(const int64_t* __restrict__ seq_off, int64_t m, int sublen, int32_t* cnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int64_t L = seq_off[i + 1] - seq_off[i];
+    cnt[i] = (int32_t)((L + sublen - 1) / sublen); // for (i = 0; i < length; i += subreadLength): split_naive.cpp:27
+}
+void launch_split_counts(const int64_t* seq_off, int64_t m, int sublen, int32_t* cnt, cudaStream_t st)
+{
+    if (m > 0) k_split_counts<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(seq_off, m, sublen, cnt);
+}
+__global__ void __launch_bounds__(256) k_split_expand(const int64_t* __restrict__ seq_off, const int64_t* __restrict__ name_off, int64_t own_first,
+                                                       int64_t m, int sublen, const int64_t* __restrict__ base, int32_t* frag_read,
+                                                       int32_t* frag_a, int32_t* frag_b, int32_t* frag_size)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t L = seq_off[i + 1] - seq_off[i];
+    const int     name_len = (int)(name_off[own_first + i + 1] - name_off[own_first + i]);
+    int64_t       g = base[i];
+    for (int64_t a0 = 0, k = 1; a0 < L; a0 += sublen, k++, g++) {
+        int64_t b0 = a0 + sublen < L ? a0 + sublen : L;
+        frag_read[g] = (int32_t)i; frag_a[g] = (int32_t)a0; frag_b[g] = (int32_t)b0;
+        frag_size[g] = (int32_t)(1 + name_len + 1 + dec_digits64((uint64_t)k) + 1 + (b0 - a0) + 1); // ">" name "_" k "\n" bases "\n"
+    }
+}
+void launch_split_expand(const int64_t* seq_off, const int64_t* name_off, int64_t own_first, int64_t m, int sublen, const int64_t* base,
+                         int32_t* frag_read, int32_t* frag_a, int32_t* frag_b, int32_t* frag_size, cudaStream_t st)
+{
+    if (m > 0) k_split_expand<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(seq_off, name_off, own_first, m, sublen, base, frag_read, frag_a, frag_b, frag_size);
+}
+
 // ---------------------------------------------------------------- repeats: text sizes + compaction
 // long_repeats.txt line: "read " i ", " then s "," e "    " per repeat, then "\n" (repeat.hpp:180-203)
 __global__ void __launch_bounds__(256) k_rep_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, int64_t m,

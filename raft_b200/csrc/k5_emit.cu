@@ -436,7 +436,21 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
                 const int64_t  nm0 = a.name_off[gid];
                 const int      nl = (int)(a.name_off[gid + 1] - nm0);
                 const int      dn = dec_digits64(num);
-                if (!a.sim) {
+                if (a.split_len > 0) {
+                    // ">" name "_" k "\n"   (split_naive.cpp:32)
+                    const unsigned kk = (unsigned)(pc.fa / a.split_len + 1);
+                    const int      dk = dec_digits(kk);
+                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
+                        int     q = (int)(x - O);
+                        uint8_t c;
+                        if (q < 1) c = '>';
+                        else if ((q -= 1) < nl) c = a.names[nm0 + q];
+                        else if ((q -= nl) < 1) c = '_';
+                        else if ((q -= 1) < dk) c = dec_digit_at32(kk, dk, q);
+                        else c = '\n';
+                        a.dst[x - a.w0] = c;
+                    }
+                } else if (!a.sim) {
                     const unsigned fa = (unsigned)pc.fa, fb = (unsigned)(pc.fa + pc.len);
                     const int      da = dec_digits(fa), db = dec_digits(fb);
                     for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {

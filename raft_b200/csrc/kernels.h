@@ -163,6 +163,10 @@ struct FragExpandArgs {
     const SimInfo* sim;         // null for real reads
 };
 void launch_frag_expand(const FragExpandArgs& a, cudaStream_t st);
+// split_naive (split_naive.cpp:27-33): piece counts per read, then (read, a, b, record bytes) per piece
+void launch_split_counts(const int64_t* seq_off, int64_t m, int sublen, int32_t* cnt, cudaStream_t st);
+void launch_split_expand(const int64_t* seq_off, const int64_t* name_off, int64_t own_first, int64_t m, int sublen, const int64_t* base,
+                         int32_t* frag_read, int32_t* frag_a, int32_t* frag_b, int32_t* frag_size, cudaStream_t st);
 // compact repeats: rep_off = exclusive scan of rep_cnt; rep_out[2*k] pairs in read order; also text size per read line
 void launch_rep_sizes(const int32_t* rep_cnt, const int64_t* rep_cap_off, const int2* rep, int64_t m, int64_t own_first, int32_t* line_size,
                       cudaStream_t st);
@@ -236,6 +240,7 @@ struct FastaEmitArgs {
     const int32_t* tile_frag; // record containing stream byte T*FASTA_TILE, for every tile of the stream
     int64_t        seq_safe_end; // bytes of the arena that may be read in 16-byte blocks (multiple of 16)
     const SimInfo* sim;          // null for real reads
+    int            split_len;    // > 0: split_naive records  ">" name "_" k "\n" bases "\n"  with k = a / split_len + 1
 };
 void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st);
 void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st);

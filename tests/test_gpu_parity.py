@@ -371,3 +371,33 @@ def test_device_fasta_ingest_full_pipeline():
     st = ctx.run()
     compare_all(ctx, st, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("sublen", [1, 13, 5000, 20000])
+def test_split_naive_stream(sublen):
+    """Row f4: split_naive.cpp through the same gather kernel; bytes equal the oracle's (pinned to the reference binary)."""
+    ds = synth.make_dataset("C1", 0.03 if sublen > 1 else 0.002, True, seed=8)
+    fa_bytes = synth.format_fasta(ds.reads) + b">empty\n\n>tail\nACGTAC\n"
+    reads = O.parse_fasta(fa_bytes)
+    want = O.split_naive(reads, sublen)
+    ctx = api.Context(api.AlgoParams(est_cov=1))
+    ctx.ingest_fasta(np.frombuffer(fa_bytes, np.uint8), len(fa_bytes), last=True)
+    ctx.split_naive(sublen)
+    assert ctx.output_size(api.OUT_SPLIT_NAIVE) == len(want)
+    assert ctx.fetch(api.OUT_SPLIT_NAIVE) == want
+    assert ctx.digest(api.OUT_SPLIT_NAIVE) == O.digest(want)
+    off = len(want) // 3
+    assert ctx.fetch(api.OUT_SPLIT_NAIVE, off, min(100000, len(want) - off)) == want[off:off + min(100000, len(want) - off)]
+    ctx.close()
+
+
+def test_split_naive_cli():
+    exe = os.path.join(ROOT, "raft_b200", "split_naive")
+    ds = synth.make_dataset("C1", 0.02, False, seed=4)
+    fa_bytes = synth.format_fasta(ds.reads, wrap=70)
+    with tempfile.TemporaryDirectory() as d:
+        fa, out = os.path.join(d, "r.fa"), os.path.join(d, "o.fa")
+        open(fa, "wb").write(fa_bytes)
+        r = subprocess.run([exe, fa, out, "7000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=120)
+        assert r.returncode == 0, r.stdout.decode()
+        assert open(out, "rb").read() == O.split_naive(ds.reads, 7000)

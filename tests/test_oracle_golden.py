@@ -87,3 +87,17 @@ def test_oracle_sim_mode_matches_reference_binary_live():
     assert res.status == 0 and res.real_reads == 0 and len(res.bed_txt) > 0
     for suf, data in zip(SUFS, (res.cov_txt, res.rep_txt, res.bed_txt, res.fasta)):
         assert files.get(suf, b"") == data, suf
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_SPLIT_BIN), reason="oracle/_ref/split_naive not built")
+@pytest.mark.parametrize("sublen", [1, 7, 20000, 1000000])
+def test_oracle_split_naive_matches_reference_binary_live(sublen):
+    import subprocess
+    ds = synth.make_dataset("C1", 0.02, True, seed=3)
+    fa_bytes = synth.format_fasta(ds.reads, wrap=60) + b">empty\n\n>tail\nACGTAC\n"
+    reads = O.parse_fasta(fa_bytes)
+    with tempfile.TemporaryDirectory() as d:
+        fa, out = os.path.join(d, "r.fa"), os.path.join(d, "o.fa")
+        open(fa, "wb").write(fa_bytes)
+        subprocess.run([O.REF_SPLIT_BIN, fa, out, str(sublen)], check=True, timeout=120)
+        assert open(out, "rb").read() == O.split_naive(reads, sublen)
