@@ -153,6 +153,12 @@ int raftgpu_get_stats(raftgpu_ctx *ctx, raftgpu_stats *stats);
  * by window.  dst [host|device]. */
 int raftgpu_output_size(raftgpu_ctx *ctx, int which, uint64_t *nbytes);
 int raftgpu_fetch(raftgpu_ctx *ctx, int which, uint64_t off, uint8_t *dst, size_t n);
+/* Asynchronous form for device destinations: the emitter is queued and the call returns; raftgpu_sync waits for
+ * everything queued and reports errors.  The text streams (coverage, long_repeats, bed) and the sequence streams
+ * (reads.fasta, split_naive) run on two different CUDA streams, so a caller that queues both lets the issue-bound text
+ * formatter overlap the bandwidth-bound gather.  Destinations of calls queued on the same stream may alias. */
+int raftgpu_fetch_async(raftgpu_ctx *ctx, int which, uint64_t off, uint8_t *dst_device, size_t n);
+int raftgpu_sync(raftgpu_ctx *ctx);
 /* Order-independent 64-bit digest of a whole output stream computed on the device
  * (sum over bytes of mix64(offset*257 + byte + 1)); used for parity at sizes the host cannot hold. */
 int raftgpu_digest(raftgpu_ctx *ctx, int which, uint64_t *digest);

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libraft_b200.so")
 SYMBOLS = [
     "raftgpu_default_params", "raftgpu_create", "raftgpu_destroy", "raftgpu_reset", "raftgpu_strerror",
     "raftgpu_last_error", "raftgpu_error_index", "raftgpu_set_option", "raftgpu_set_reads", "raftgpu_ingest_fasta", "raftgpu_load_fasta", "raftgpu_free_host",
-    "raftgpu_split_naive", "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_digest",
+    "raftgpu_split_naive", "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_fetch_async", "raftgpu_sync", "raftgpu_digest",
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
     "raftgpu_accumulate_local", "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
@@ -68,6 +68,8 @@ def lib():
         "raftgpu_get_stats": (C.c_int, [vp, PS]),
         "raftgpu_output_size": (C.c_int, [vp, C.c_int, C.POINTER(u64)]),
         "raftgpu_fetch": (C.c_int, [vp, C.c_int, u64, vp, sz]),
+        "raftgpu_fetch_async": (C.c_int, [vp, C.c_int, u64, vp, sz]),
+        "raftgpu_sync": (C.c_int, [vp]),
         "raftgpu_digest": (C.c_int, [vp, C.c_int, C.POINTER(u64)]),
         "raftgpu_fetch_table": (C.c_int, [vp, C.c_int, vp, sz, C.POINTER(sz)]),
         "raftgpu_set_reads_sharded": (C.c_int, [vp, i64, vp, vp, vp, i64, i64, vp, vp]),

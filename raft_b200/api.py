@@ -171,6 +171,13 @@ class Context:
     def fetch_into(self, which, off, dst, n):
         self._ck(self.L.raftgpu_fetch(self._h, which, off, _ptr(dst), n))
 
+    def fetch_async(self, which, off, dst, n):
+        """Queue the emitter for a device destination; pair with sync()."""
+        self._ck(self.L.raftgpu_fetch_async(self._h, which, off, _ptr(dst), n))
+
+    def sync(self):
+        self._ck(self.L.raftgpu_sync(self._h))
+
     def digest(self, which) -> int:
         d = C.c_uint64()
         self._ck(self.L.raftgpu_digest(self._h, which, C.byref(d)))

@@ -112,9 +112,12 @@ struct raftgpu_ctx {
     DevBuf  b_stage[2];
     cudaEvent_t ev[8]{};
     cudaEvent_t ev_stage[2]{};
-    cudaEvent_t ev_emit[2]{};
-    bool        emit_pending = false;
-    int         emit_pending_which = 0;
+    // two emit lanes so that the issue-bound text emitters and the bandwidth-bound gather can overlap:
+    // lane 0 (stream st_aux): coverage.txt, long_repeats.txt, .bed;  lane 1 (stream st): reads.fasta, split_naive
+    struct EmitLane { cudaStream_t st = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool open = false; int kind = 0; };
+    EmitLane     lane[2];
+    bool         emit_shared_gpu = false; // asynchronous emission: leave SM slots for the other lane
+    cudaStream_t st_aux = nullptr;
 
     // split_naive stream (raftgpu_split_naive)
     int      sn_len = 0;
@@ -220,7 +223,9 @@ int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) return bail();
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
-    for (auto& e : ctx->ev_emit) if (cudaEventCreate(&e) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    ctx->lane[0].st = ctx->st_aux; ctx->lane[1].st = ctx->st;
+    for (auto& L : ctx->lane) if (cudaEventCreate(&L.ev0) != cudaSuccess || cudaEventCreate(&L.ev1) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (ctx->b_misc.ensure(sizeof(Misc)) != cudaSuccess) return bail();
     *out = ctx;
@@ -234,7 +239,8 @@ int raftgpu_destroy(raftgpu_ctx* ctx)
     cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
-    for (auto& e : ctx->ev_emit) if (e) cudaEventDestroy(e);
+    for (auto& L : ctx->lane) { if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
+    if (ctx->st_aux) { cudaStreamSynchronize(ctx->st_aux); cudaStreamDestroy(ctx->st_aux); }
     if (ctx->st_h2d) { cudaStreamSynchronize(ctx->st_h2d); cudaStreamDestroy(ctx->st_h2d); }
     for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
@@ -260,7 +266,7 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     ctx->sn_len = 0; ctx->sn_G = 0; ctx->sn_bytes = 0;
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
-    ctx->emit_pending = false;
+    for (auto& L : ctx->lane) { if (L.open) cudaStreamSynchronize(L.st); L.open = false; }
     return RAFTGPU_OK;
 }
 
@@ -1063,30 +1069,31 @@ extern "C" int raftgpu_run(raftgpu_ctx* ctx, raftgpu_stats* out)
 // ------------------------------------------------------------------------------------------------ outputs
 // materialise stream bytes [w0, w1) of `which` at device address d (d[k] = stream byte w0+k)
 static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st);
-static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st)
+static inline int lane_of(int which) { return (which == RAFTGPU_OUT_READS_FASTA || which == RAFTGPU_OUT_SPLIT_NAIVE) ? 1 : 0; }
+// close a lane's timing span: device time between its first launch since the last flush and its last launch
+static void lane_flush(raftgpu_ctx* ctx, int li)
 {
-    if (w1 <= w0) return RAFTGPU_OK;
-    // the previous window's events have completed by now or are waited for here (cheap: same stream)
-    if (ctx->emit_pending) {
-        cudaEventSynchronize(ctx->ev_emit[1]);
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev_emit[0], ctx->ev_emit[1]) == cudaSuccess) ctx->stats.ms_emit[ctx->emit_pending_which] += ms;
-        ctx->emit_pending = false;
-    }
-    cudaEventRecord(ctx->ev_emit[0], st);
-    int rc = emit_window_impl(ctx, which, w0, w1, d, st);
-    cudaEventRecord(ctx->ev_emit[1], st);
-    ctx->emit_pending = true; ctx->emit_pending_which = which > 3 ? 3 : which; // the split_naive stream is accounted with the gather kernel
-    ctx->stats.emit_launches[which > 3 ? 3 : which]++; ctx->stats.emit_bytes[which > 3 ? 3 : which] += (uint64_t)(w1 - w0);
-    return rc;
-}
-static void flush_emit_timer(raftgpu_ctx* ctx)
-{
-    if (!ctx->emit_pending) return;
-    cudaEventSynchronize(ctx->ev_emit[1]);
+    auto& L = ctx->lane[li];
+    if (!L.open) return;
+    cudaEventSynchronize(L.ev1);
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev_emit[0], ctx->ev_emit[1]) == cudaSuccess) ctx->stats.ms_emit[ctx->emit_pending_which] += ms;
-    ctx->emit_pending = false;
+    if (cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess) ctx->stats.ms_emit[L.kind] += ms;
+    L.open = false;
+}
+static void flush_emit_timer(raftgpu_ctx* ctx) { lane_flush(ctx, 0); lane_flush(ctx, 1); }
+// launch the emitter of stream `which` for bytes [w0, w1) on its lane's CUDA stream (no host synchronisation)
+static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, bool shared_gpu = false)
+{
+    ctx->emit_shared_gpu = shared_gpu;
+    if (w1 <= w0) return RAFTGPU_OK;
+    const int li = lane_of(which), kind = which > 3 ? 3 : which; // the split_naive stream is accounted with the gather kernel
+    auto&     L = ctx->lane[li];
+    if (L.open && L.kind != kind) lane_flush(ctx, li);
+    if (!L.open) { cudaEventRecord(L.ev0, L.st); L.open = true; L.kind = kind; }
+    int rc = emit_window_impl(ctx, which, w0, w1, d, L.st);
+    cudaEventRecord(L.ev1, L.st);
+    ctx->stats.emit_launches[kind]++; ctx->stats.emit_bytes[kind] += (uint64_t)(w1 - w0);
+    return rc;
 }
 static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, cudaStream_t st)
 {
@@ -1102,6 +1109,9 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
         ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
         ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0; ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
+        // measured: throttling the text emitter to leave SM slots for the gather (2 CTAs/SM) doubles its time and the two
+        // kernels still do not co-reside (the gather's 4 x 256 x 64 registers fill the register file), so it keeps all slots
+        ca.ctas_per_sm = 6;
         launch_cov_emit(ca, t1 - t0, st);
         CKL();
     } else if (which == RAFTGPU_OUT_LONG_REPEATS) {
@@ -1242,9 +1252,10 @@ extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t*
     if (off > stream_bytes || n > stream_bytes - off) return RAFTGPU_E_ARG;
     if (!n) return RAFTGPU_OK;
     CK(cudaSetDevice(ctx->device));
+    cudaStream_t ls = ctx->lane[lane_of(which)].st;
     if (is_device_ptr(dst)) {
-        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst, ctx->st))) return st;
-        CK(cudaStreamSynchronize(ctx->st));
+        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst))) return st;
+        CK(cudaStreamSynchronize(ls));
         return fetch_err(ctx);
     }
     // host destination: double-buffered windows, emit on st, copy out on st2
@@ -1256,14 +1267,37 @@ extern "C" int raftgpu_fetch(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t*
     while (done < n) {
         size_t len = std::min(W, n - done);
         if (used[k]) CK(cudaEventSynchronize(ctx->ev_stage[k])); // the copy out of this buffer has finished
-        if ((st = emit_window(ctx, which, (int64_t)(off + done), (int64_t)(off + done + len), ctx->b_stage[k].as<uint8_t>(), ctx->st))) return st;
-        CK(cudaStreamSynchronize(ctx->st));
+        if ((st = emit_window(ctx, which, (int64_t)(off + done), (int64_t)(off + done + len), ctx->b_stage[k].as<uint8_t>()))) return st;
+        CK(cudaStreamSynchronize(ls));
         CK(cudaMemcpyAsync(dst + done, ctx->b_stage[k].p, len, cudaMemcpyDeviceToHost, ctx->st2));
         CK(cudaEventRecord(ctx->ev_stage[k], ctx->st2));
         used[k] = true;
         done += len; k ^= 1;
     }
     CK(cudaStreamSynchronize(ctx->st2));
+    return fetch_err(ctx);
+}
+
+extern "C" int raftgpu_fetch_async(raftgpu_ctx* ctx, int which, uint64_t off, uint8_t* dst_device, size_t n)
+{
+    if (!ctx || which < 0 || which > 4 || (!dst_device && n)) return RAFTGPU_E_ARG;
+    uint64_t stream_bytes = 0;
+    int      st = raftgpu_output_size(ctx, which, &stream_bytes);
+    if (st) return st;
+    if (off > stream_bytes || n > stream_bytes - off) return RAFTGPU_E_ARG;
+    if (!n) return RAFTGPU_OK;
+    if (!is_device_ptr(dst_device)) FAIL(RAFTGPU_E_ARG, "raftgpu_fetch_async needs a device destination");
+    CK(cudaSetDevice(ctx->device));
+    return emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst_device, true);
+}
+
+extern "C" int raftgpu_sync(raftgpu_ctx* ctx)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st_aux));
+    CK(cudaStreamSynchronize(ctx->st));
+    flush_emit_timer(ctx);
     return fetch_err(ctx);
 }
 
@@ -1276,15 +1310,18 @@ extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest)
     CK(cudaSetDevice(ctx->device));
     const size_t   W = (size_t)std::min<uint64_t>(WINDOW_BYTES, std::max<uint64_t>(total, 1));
     CK(ctx->b_stage[0].ensure(W + 64));
-    CK(cudaMemsetAsync(&ctx->misc()->digest, 0, sizeof(unsigned long long), ctx->st));
+    cudaStream_t ls = ctx->lane[lane_of(which)].st;
+    CK(cudaStreamSynchronize(ctx->st)); CK(cudaStreamSynchronize(ctx->st_aux));
+    CK(cudaMemsetAsync(&ctx->misc()->digest, 0, sizeof(unsigned long long), ls));
     for (uint64_t off = 0; off < total; off += W) {
         size_t len = (size_t)std::min<uint64_t>(W, total - off);
-        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + len), ctx->b_stage[0].as<uint8_t>(), ctx->st))) return st;
-        launch_digest(ctx->b_stage[0].as<uint8_t>(), (int64_t)len, (int64_t)off, &ctx->misc()->digest, ctx->st);
+        if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + len), ctx->b_stage[0].as<uint8_t>()))) return st;
+        launch_digest(ctx->b_stage[0].as<uint8_t>(), (int64_t)len, (int64_t)off, &ctx->misc()->digest, ls);
         CKL();
     }
     unsigned long long d = 0;
-    CK(cudaMemcpyAsync(&d, &ctx->misc()->digest, sizeof d, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&d, &ctx->misc()->digest, sizeof d, cudaMemcpyDeviceToHost, ls));
+    CK(cudaStreamSynchronize(ls));
     if ((st = fetch_err(ctx))) return st;
     *digest = d;
     return RAFTGPU_OK;

@@ -53,11 +53,8 @@ __device__ __forceinline__ uint8_t* cov_format_slots(uint8_t* p, SlotWalk w, int
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitArgs a)
+__device__ __forceinline__ void cov_text_tile(const CovEmitArgs& a, const int64_t tile, uint8_t* sbuf, int* ws)
 {
-    extern __shared__ __align__(16) uint8_t sbuf[];
-    __shared__ int ws[34];
-    const int64_t  tile = a.tile_first + blockIdx.x;
     const int64_t  g0 = tile * COV_TILE_SLOTS + (int64_t)threadIdx.x * CE_PER;
     const int      nmine = g0 >= a.n_slots ? 0 : (a.n_slots - g0 < CE_PER ? (int)(a.n_slots - g0) : CE_PER);
     int            mine = 0;
@@ -120,6 +117,19 @@ __global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitAr
     for (uintptr_t x = la + threadIdx.x; x < ga1; x += CE_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
 }
 
+// Persistent over tiles [tile_first, tile_first + n_tiles): the grid is sized by the launcher (all SM slots when the
+// emitter runs alone, two CTAs per SM when it shares the GPU with the gather kernel on the other emit stream).
+template <bool EMIT>
+__global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitArgs a, int64_t n_tiles)
+{
+    extern __shared__ __align__(16) uint8_t sbuf[];
+    __shared__ int ws[34];
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        cov_text_tile<EMIT>(a, a.tile_first + t, sbuf, ws);
+        __syncthreads(); // the shared text buffer and the scan scratch are reused by the next tile
+    }
+}
+
 // one thread per read: every tile whose first slot lies in this read's slot range points at it
 __global__ void __launch_bounds__(256) k_cov_tile_index(const int64_t* __restrict__ slot_off, int64_t m, int64_t n_tiles, int32_t* tile_read)
 {
@@ -139,7 +149,7 @@ int  cov_tiles(int64_t n_slots) { return (int)((n_slots + COV_TILE_SLOTS - 1) / 
 void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st)
 {
     int t = cov_tiles(a.n_slots);
-    if (t > 0) k_cov_text<false><<<t, CE_THREADS, 0, st>>>(a);
+    if (t > 0) k_cov_text<false><<<t, CE_THREADS, 0, st>>>(a, (int64_t)t);
 }
 void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream_t st)
 {
@@ -148,7 +158,9 @@ void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream
     a.text_cap = CE_CAP;
     if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CE_CAP) a.text_cap = v; } // test knob: force the direct path
     cudaFuncSetAttribute(k_cov_text<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
-    k_cov_text<true><<<(unsigned)n_tiles_launch, CE_THREADS, CE_SMEM, st>>>(a);
+    const int64_t per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : 6;
+    const int64_t grid = n_tiles_launch < 148 * per_sm ? n_tiles_launch : 148 * per_sm;
+    k_cov_text<true><<<(unsigned)grid, CE_THREADS, CE_SMEM, st>>>(a, n_tiles_launch);
 }
 
 // ================================================================ K5c long_repeats.txt

@@ -150,6 +150,7 @@ def bench(a, rank, world, local, log):
     log(f"[bench r{rank}] reads {b0}..{b1} of {ds.n}, {own_seq.numel()} bases, local PAF {ds.paf.numel()} bytes / {ds.n_overlaps} lines")
     ctx = api.Context(p, local)
     win = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
+    win2 = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
 
     def step(host=None):
         if host is None:
@@ -161,11 +162,19 @@ def bench(a, rank, world, local, log):
             st, info = run_rank(ctx, comm, bounds, host["paf"], ds.paf.numel())
             dst = host["out"].data_ptr()
         nout = 0
-        for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
-            n = ctx.output_size(which)
-            for off in range(0, n, WINDOW):
-                ctx.fetch_into(which, off, dst, min(WINDOW, n - off))
-            nout += n
+        if host is None:  # device windows: text streams and the gather overlap on the library's two emit streams
+            for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+                n = ctx.output_size(which)
+                for off in range(0, n, WINDOW):
+                    ctx.fetch_async(which, off, win2 if which != api.OUT_READS_FASTA else win, min(WINDOW, n - off))
+                nout += n
+            ctx.sync()
+        else:
+            for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+                n = ctx.output_size(which)
+                for off in range(0, n, WINDOW):
+                    ctx.fetch_into(which, off, dst, min(WINDOW, n - off))
+                nout += n
         return st, info, nout
 
     def timed(k, host=None):
