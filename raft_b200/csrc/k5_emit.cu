@@ -255,31 +255,35 @@ void launch_bed_emit(const RepEmitArgs& a, cudaStream_t st)
 
 // ================================================================ K5b reads.fasta
 // Output-tile-parallel gather, persistent and warp-specialised.  A tile is 16 KiB of the reads.fasta stream.
-// Warp 0 (one lane) is the producer: for each tile it walks the records that intersect it (tile_frag[T] gives
-// the first, FragDesc has everything else in one 32-byte load), writes a piece list into the next free
-// pipeline slot and issues one 1-D TMA bulk copy per sequence piece from the read arena into that slot's
-// stage buffer (a 16-byte aligned superset of the piece).  Warps 1..7 are consumers: they wait on the
-// slot's `full` mbarrier (producer arrive + TMA transaction bytes), generate the few header bytes,
-// realign the staged bases (two aligned 128-bit shared loads + funnel shifts) into aligned 128-bit
-// streaming stores, and release the slot through its `empty` mbarrier.  With two slots the walk and the
-// TMA latency of tile i+1 hide behind the stores of tile i.
+// Warp 0 is the producer.  For each tile its 32 lanes load 32 consecutive FragDesc entries starting at
+// tile_frag[T] (one coalesced request; the entries of the NEXT tile are already in flight while the current
+// one is laid out), a ballot + warp scan turns the records that intersect the tile into a piece list in the
+// next free pipeline slot, and every lane issues the 1-D TMA bulk copy of its own piece from the read arena
+// into that slot's stage buffer (a 16-byte aligned superset of the piece).  A lane whose record's header
+// starts in the tile also fetches the name extent, so the consumers never chase name_off.  Warps 1..7 are
+// consumers: they wait on the slot's `full` mbarrier (producer arrive + TMA transaction bytes), generate the
+// few header bytes, realign the staged bases (two aligned 128-bit shared loads + funnel shifts) into aligned
+// 128-bit streaming stores, and release the slot through its `empty` mbarrier.  Three slots keep two tiles
+// of loads in flight per CTA behind the tile being stored.
 constexpr int FE_THREADS = 256;
 constexpr int FE_CONSUMERS = FE_THREADS - 32;       // 7 warps
-constexpr int FE_SLOTS = 2;
-constexpr int FE_MAXP = 24;                         // pieces per slot
-constexpr int FE_STAGE = FASTA_TILE + FE_MAXP * 32; // staged source bytes per slot
+constexpr int FE_SLOTS = 3;
+constexpr int FE_MAXP = 32;                         // pieces per slot (one producer round)
+constexpr int FE_STAGE = FASTA_TILE + 512;          // staged source bytes per slot (alignment slack; overflow spills to the next slot)
 
 struct FePiece {
-    long long frag;   // record index
-    long long O;      // stream offset of the record
-    long long p0;     // stream position of the first sequence byte of the piece
-    const uint8_t* src; // global address of that byte
-    int       n;      // sequence bytes of the piece inside the tile (0: header / newline only)
+    long long O;       // stream offset of the record
+    const uint8_t* src; // global address of the first sequence byte of the piece
+    long long nm0;     // offset of the read's name in `names`
+    int       frag;    // record index
+    int       n;       // sequence bytes of the piece inside the tile (0: header / newline only)
     int       n_stage; // leading bytes available in shared memory (the rest is read from global)
-    int       soff;   // offset of the first byte in the stage buffer
-    int       bulk;   // bytes moved by the piece's TMA copy
+    int       soff;    // offset of the first byte in the stage buffer
     int       h, len, read, fa;
+    int       nl;      // name length
+    int       pad;
 };
+static_assert(sizeof(FePiece) == 64, "FePiece layout");
 
 struct __align__(16) FeSmem {
     uint8_t   stage[FE_SLOTS][FE_STAGE];
@@ -288,6 +292,7 @@ struct __align__(16) FeSmem {
     int       np[FE_SLOTS]; // -1: no more work
     uint64_t  full[FE_SLOTS], empty[FE_SLOTS];
 };
+static_assert(4 * (sizeof(FeSmem) + 1024) <= 228 * 1024, "four CTAs per SM");
 
 // consumer threads (index ct of FE_CONSUMERS): n bytes from shared memory (any alignment) to global (any alignment)
 __device__ __forceinline__ void consumers_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n, int ct)
@@ -349,6 +354,57 @@ void launch_frag_sample(const FragDesc* desc, int64_t G, int step, int64_t* out2
     k_frag_sample<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(desc, G, step, out2);
 }
 
+// Header bytes of one record (all modes).  q indexes the header, 0 = '>'.
+struct FeHeader {
+    uint64_t       num;      // read= number
+    const uint8_t* name;     // read name
+    int            nl, dn;
+    unsigned       fa, fb, kk;
+    int            da, db, dk;
+    int            vx, vy, vl, dx, dy, dl, align_off, align_len, tail_off, tl;
+};
+__device__ __forceinline__ uint8_t fe_signed_char_at(int v, int nd, int q)
+{
+    if (v < 0) { if (q == 0) return '-'; return dec_digit_at32((uint32_t)(-(int64_t)v), nd - 1, q - 1); }
+    return dec_digit_at32((uint32_t)v, nd, q);
+}
+template <int MODE> // 0 real, 1 sim, 2 split_naive
+__device__ __forceinline__ uint8_t fe_header_char(const FeHeader& H, int q)
+{
+    if (MODE == 2) {
+        // ">" name "_" k "\n"   (split_naive.cpp:32)
+        if (q < 1) return '>';
+        if ((q -= 1) < H.nl) return H.name[q];
+        if ((q -= H.nl) < 1) return '_';
+        if ((q -= 1) < H.dk) return dec_digit_at32(H.kk, H.dk, q);
+        return '\n';
+    }
+    if (q < 6) return (uint8_t)(">read="[q]);
+    if ((q -= 6) < H.dn) return (H.num >> 32) ? dec_digit_at(H.num, H.dn, q) : dec_digit_at32((uint32_t)H.num, H.dn, q);
+    if ((q -= H.dn) < 1) return ',';
+    q -= 1;
+    if (MODE == 0) {
+        // ">read=" num "," name ",pos_on_original_read=" a "-" b "\n"   (chop.hpp:261-265, 314-318)
+        if (q < H.nl) return H.name[q];
+        if ((q -= H.nl) < 22) return (uint8_t)(",pos_on_original_read="[q]);
+        if ((q -= 22) < H.da) return dec_digit_at32(H.fa, H.da, q);
+        if ((q -= H.da) < 1) return '-';
+        if ((q -= 1) < H.db) return dec_digit_at32(H.fb, H.db, q);
+        return '\n';
+    }
+    // ">read=" num "," align ",position=" x "-" y ",length=" ln tail "\n"   (chop.hpp:252-258, 293-310)
+    if (q < H.align_len) return H.name[H.align_off + q];
+    if ((q -= H.align_len) < 10) return (uint8_t)(",position="[q]);
+    if ((q -= 10) < H.dx) return fe_signed_char_at(H.vx, H.dx, q);
+    if ((q -= H.dx) < 1) return '-';
+    if ((q -= 1) < H.dy) return fe_signed_char_at(H.vy, H.dy, q);
+    if ((q -= H.dy) < 8) return (uint8_t)(",length="[q]);
+    if ((q -= 8) < H.dl) return fe_signed_char_at(H.vl, H.dl, q);
+    if ((q -= H.dl) < H.tl) return H.name[H.tail_off + q];
+    return '\n';
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, int64_t n_tiles)
 {
     extern __shared__ __align__(16) uint8_t fe_raw[];
@@ -360,67 +416,91 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
     const int64_t T0 = a.w0 / FASTA_TILE;
 
     if (threadIdx.x < 32) {
-        // ================= producer (one lane) =================
-        if (threadIdx.x != 0) return;
-        int      slot = 0;
-        unsigned ph = 0;
-        for (int64_t t = blockIdx.x;; t += gridDim.x) {
+        // ================= producer warp =================
+        const int      lane = threadIdx.x;
+        const unsigned lt = (1u << lane) - 1u;
+        int            slot = 0;
+        unsigned       ph = 0;
+        const int64_t  step = gridDim.x;
+        auto load_desc = [&](int64_t g) {
+            FragDesc d;
+            if (g <= a.G) d = a.desc[g];                       // entry G: out_off = stream length (a terminator)
+            else { d.out_off = INT64_MAX / 2; d.src_off = 0; d.len = 0; d.hdr_len = 0; d.read = 0; d.a = 0; }
+            return d;
+        };
+        // software pipeline: tile_frag two tiles ahead, descriptors one tile ahead
+        int64_t  t = blockIdx.x;
+        int64_t  g_cur = t < n_tiles ? a.tile_frag[T0 + t] : 0;
+        int64_t  g_nxt = t + step < n_tiles ? a.tile_frag[T0 + t + step] : 0;
+        FragDesc d_cur = load_desc(t < n_tiles ? g_cur + lane : INT64_MAX);
+        for (;; t += step) {
             const bool    done = t >= n_tiles;
             const int64_t T = T0 + t, xs = T * FASTA_TILE;
             const int64_t x0 = xs > a.w0 ? xs : a.w0;
             const int64_t x1 = (xs + FASTA_TILE) < a.w1 ? (xs + FASTA_TILE) : a.w1;
-            int64_t       g = done ? 0 : a.tile_frag[T]; // record containing the tile's first byte
-            bool          more = true;
+            int64_t       g = g_cur;                    // record containing the tile's first byte
+            FragDesc      d = d_cur;
+            g_cur = g_nxt;
+            g_nxt = t + 2 * step < n_tiles ? a.tile_frag[T0 + t + 2 * step] : 0;
+            d_cur = load_desc(t + step < n_tiles ? g_cur + lane : INT64_MAX);
+            bool more = true, first = true;
             while (more) {
+                if (!first) d = load_desc(g + lane);
+                first = false;
                 mbar_wait(&s.empty[slot], ph ^ 1);   // the consumers are done with this slot's previous contents
-                int np = 0, used = 0;
-                more = false;
                 if (done) {
-                    np = -1;
-                } else {
-                    FePiece* pl = s.piece[slot];
-                    for (; g < a.G; g++) {
-                        const FragDesc d = a.desc[g];
-                        const int64_t  O = d.out_off;
-                        if (O >= x1) break;
-                        const int64_t s0 = O + d.hdr_len, s1 = s0 + d.len;
-                        if (s1 + 1 <= x0) continue;                               // the window starts after this record
-                        if (np == FE_MAXP) { more = true; break; }
-                        const int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
-                        FePiece&      pc = pl[np];
-                        pc.frag = g; pc.O = O; pc.p0 = p0; pc.n = p1 > p0 ? (int)(p1 - p0) : 0; pc.n_stage = 0; pc.soff = 0; pc.bulk = 0; pc.src = nullptr;
-                        pc.h = d.hdr_len; pc.len = d.len; pc.read = d.read; pc.fa = d.a;
-                        if (pc.n > 0) {
-                            const int64_t srcoff = d.src_off + (p0 - s0);         // offset in the arena
-                            const int64_t al = srcoff & ~(int64_t)15;
-                            int64_t       end = (srcoff + pc.n + 15) & ~(int64_t)15;
-                            if (end > a.seq_safe_end) end = a.seq_safe_end;       // never read past what the arena guarantees
-                            const int bytes = end > al ? (int)(end - al) : 0;
-                            if (used + bytes > FE_STAGE) { more = true; break; }  // another slot for the rest of this tile
-                            pc.src = a.seq + srcoff;
-                            pc.soff = used + (int)(srcoff - al);
-                            const int avail = bytes - (int)(srcoff - al);
-                            pc.n_stage = avail < 0 ? 0 : (avail > pc.n ? pc.n : avail);
-                            pc.bulk = bytes;
-                            used += bytes;
-                        }
-                        np++;
-                    }
+                    if (lane == 0) { s.np[slot] = -1; mbar_arrive(&s.full[slot]); }
+                    break;
                 }
-                s.np[slot] = np; s.x0[slot] = x0; s.x1[slot] = x1;
-                if (used > 0) {
-                    mbar_expect_tx(&s.full[slot], (uint32_t)used); // arrive (release: the list above is visible) + expected bytes
-                    int off = 0;
-                    for (int k = 0; k < np; k++) {
-                        const FePiece& pc = s.piece[slot][k];
-                        if (pc.bulk > 0) {
-                            tma_load_1d(s.stage[slot] + off, pc.src - (pc.soff - off), (uint32_t)pc.bulk, &s.full[slot]);
-                            off += pc.bulk;
-                        }
+                const int64_t O = d.out_off;
+                const bool    valid = O < x1;
+                const int64_t s0 = O + d.hdr_len, s1 = s0 + d.len;
+                const bool    emit = valid && s1 + 1 > x0;                    // else the window starts after this record
+                const int64_t p0 = s0 > x0 ? s0 : x0, p1 = s1 < x1 ? s1 : x1;
+                const int     n = emit && p1 > p0 ? (int)(p1 - p0) : 0;
+                const int64_t srcoff = d.src_off + (p0 - s0);                 // offset in the arena
+                const int64_t al = srcoff & ~(int64_t)15;
+                int64_t       end = (srcoff + n + 15) & ~(int64_t)15;
+                if (end > a.seq_safe_end) end = a.seq_safe_end;               // never read past what the arena guarantees
+                const int      bytes = n > 0 && end > al ? (int)(end - al) : 0;
+                const int      incl = warp_inclusive_sum(bytes);
+                const unsigned emit_m = __ballot_sync(0xffffffffu, emit);
+                const int      idx = __popc(emit_m & lt);
+                const unsigned nofit_m = __ballot_sync(0xffffffffu, emit && (idx >= FE_MAXP || incl > FE_STAGE));
+                const unsigned inval_m = __ballot_sync(0xffffffffu, !valid);
+                const int      cut = nofit_m ? __ffs(nofit_m) - 1 : 32;       // lane 0 always fits
+                const int      fin = inval_m ? __ffs(inval_m) - 1 : 32;
+                const int64_t  gb = g;
+                int            limit;
+                if (fin < 32 && fin <= cut) { limit = fin; more = false; }
+                else { limit = cut; g += cut; }                               // another slot for the rest of this tile
+                const unsigned lim_m = limit >= 32 ? 0xffffffffu : ((1u << limit) - 1u);
+                const int      used = limit > 0 ? __shfl_sync(0xffffffffu, incl, limit - 1) : 0;
+                const bool     mine = emit && lane < limit;
+                if (mine) {
+                    FePiece& pc = s.piece[slot][idx];
+                    const int soff = incl - bytes + (int)(srcoff - al);
+                    const int avail = bytes - (int)(srcoff - al);
+                    pc.O = O; pc.src = a.seq + srcoff; pc.frag = (int)(gb + lane); pc.n = n;
+                    pc.n_stage = avail < 0 ? 0 : (avail > n ? n : avail); pc.soff = soff;
+                    pc.h = d.hdr_len; pc.len = d.len; pc.read = d.read; pc.fa = d.a;
+                    long long nm0 = 0;
+                    int       nl = 0;
+                    if (O < x1 && s0 > x0) {                                  // some header byte lies in the window
+                        const int64_t gid = a.own_first + d.read;
+                        nm0 = a.name_off[gid];
+                        nl = (int)(a.name_off[gid + 1] - nm0);
                     }
-                } else {
-                    mbar_arrive(&s.full[slot]);
+                    pc.nm0 = nm0; pc.nl = nl;
                 }
+                if (lane == 0) { s.np[slot] = __popc(emit_m & lim_m); s.x0[slot] = x0; s.x1[slot] = x1; }
+                __syncwarp();
+                if (lane == 0) {
+                    if (used > 0) mbar_expect_tx(&s.full[slot], (uint32_t)used); // arrive (release: the list above is visible) + expected bytes
+                    else mbar_arrive(&s.full[slot]);
+                }
+                __syncwarp();
+                if (mine && bytes > 0) tma_load_1d(s.stage[slot] + (incl - bytes), a.seq + al, (uint32_t)bytes, &s.full[slot]);
                 if (++slot == FE_SLOTS) { slot = 0; ph ^= 1; }
             }
             if (done) break;
@@ -442,80 +522,37 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
             const int64_t  O = pc.O;
             const int      h = pc.h;
             const int64_t  hp0 = O > x0 ? O : x0, hp1 = (O + h) < x1 ? (O + h) : x1;
-            if (hp0 < hp1) {
-                const int64_t  gid = a.own_first + pc.read;
-                const uint64_t num = (uint64_t)(a.read_num_base + pc.frag + 1);
-                const int64_t  nm0 = a.name_off[gid];
-                const int      nl = (int)(a.name_off[gid + 1] - nm0);
-                const int      dn = dec_digits64(num);
-                if (a.split_len > 0) {
-                    // ">" name "_" k "\n"   (split_naive.cpp:32)
-                    const unsigned kk = (unsigned)(pc.fa / a.split_len + 1);
-                    const int      dk = dec_digits(kk);
-                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
-                        int     q = (int)(x - O);
-                        uint8_t c;
-                        if (q < 1) c = '>';
-                        else if ((q -= 1) < nl) c = a.names[nm0 + q];
-                        else if ((q -= nl) < 1) c = '_';
-                        else if ((q -= 1) < dk) c = dec_digit_at32(kk, dk, q);
-                        else c = '\n';
-                        a.dst[x - a.w0] = c;
-                    }
-                } else if (!a.sim) {
-                    const unsigned fa = (unsigned)pc.fa, fb = (unsigned)(pc.fa + pc.len);
-                    const int      da = dec_digits(fa), db = dec_digits(fb);
-                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
-                        int     q = (int)(x - O);
-                        uint8_t c;
-                        if (q < 6) c = (uint8_t)(">read="[q]);
-                        else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
-                        else if ((q -= dn) < 1) c = ',';
-                        else if ((q -= 1) < nl) c = a.names[nm0 + q];
-                        else if ((q -= nl) < 22) c = (uint8_t)(",pos_on_original_read="[q]);
-                        else if ((q -= 22) < da) c = dec_digit_at32(fa, da, q);
-                        else if ((q -= da) < 1) c = '-';
-                        else if ((q -= 1) < db) c = dec_digit_at32(fb, db, q);
-                        else c = '\n';
-                        a.dst[x - a.w0] = c;
-                    }
+            // the header byte this thread owns is computed first (its name load is in flight during the copy
+            // below) and stored last; headers longer than the consumer group are finished on the spot
+            uint8_t hc = 0;
+            bool    hv = false;
+            if (hp0 + ct < hp1) {
+                FeHeader H;
+                H.num = (uint64_t)(a.read_num_base + pc.frag + 1);
+                H.name = a.names + pc.nm0; H.nl = pc.nl; H.dn = dec_digits64(H.num);
+                if (MODE == 2) {
+                    H.kk = (unsigned)(pc.fa / a.split_len + 1); H.dk = dec_digits(H.kk);
+                } else if (MODE == 0) {
+                    H.fa = (unsigned)pc.fa; H.fb = (unsigned)(pc.fa + pc.len); H.da = dec_digits(H.fa); H.db = dec_digits(H.fb);
                 } else {
-                    // ">read=" num "," align ",position=" x "-" y ",length=" ln tail "\n"   (chop.hpp:252-258, 293-310)
                     const SimInfo si = a.sim[pc.read];
                     const int     L = (int)(a.seq_off[pc.read + 1] - a.seq_off[pc.read]);
-                    int           vx, vy, vl;
-                    sim_header_numbers(si, pc.len == L && pc.fa == 0, pc.fa, pc.fa + pc.len, L, &vx, &vy, &vl);
-                    const int dx = dec_len_i32(vx), dy = dec_len_i32(vy), dl = dec_len_i32(vl), tl = nl - si.tail_off;
-                    auto signed_char_at = [](int v, int nd, int q) -> uint8_t {
-                        if (v < 0) { if (q == 0) return '-'; return dec_digit_at32((uint32_t)(-(int64_t)v), nd - 1, q - 1); }
-                        return dec_digit_at32((uint32_t)v, nd, q);
-                    };
-                    for (int64_t x = hp0 + ct; x < hp1; x += FE_CONSUMERS) {
-                        int     q = (int)(x - O);
-                        uint8_t c;
-                        if (q < 6) c = (uint8_t)(">read="[q]);
-                        else if ((q -= 6) < dn) c = (num >> 32) ? dec_digit_at(num, dn, q) : dec_digit_at32((uint32_t)num, dn, q);
-                        else if ((q -= dn) < 1) c = ',';
-                        else if ((q -= 1) < si.align_len) c = a.names[nm0 + si.align_off + q];
-                        else if ((q -= si.align_len) < 10) c = (uint8_t)(",position="[q]);
-                        else if ((q -= 10) < dx) c = signed_char_at(vx, dx, q);
-                        else if ((q -= dx) < 1) c = '-';
-                        else if ((q -= 1) < dy) c = signed_char_at(vy, dy, q);
-                        else if ((q -= dy) < 8) c = (uint8_t)(",length="[q]);
-                        else if ((q -= 8) < dl) c = signed_char_at(vl, dl, q);
-                        else if ((q -= dl) < tl) c = a.names[nm0 + si.tail_off + q];
-                        else c = '\n';
-                        a.dst[x - a.w0] = c;
-                    }
+                    sim_header_numbers(si, pc.len == L && pc.fa == 0, pc.fa, pc.fa + pc.len, L, &H.vx, &H.vy, &H.vl);
+                    H.dx = dec_len_i32(H.vx); H.dy = dec_len_i32(H.vy); H.dl = dec_len_i32(H.vl);
+                    H.align_off = si.align_off; H.align_len = si.align_len; H.tail_off = si.tail_off; H.tl = pc.nl - si.tail_off;
                 }
+                hc = fe_header_char<MODE>(H, (int)(hp0 + ct - O));
+                hv = true;
+                for (int64_t x = hp0 + ct + FE_CONSUMERS; x < hp1; x += FE_CONSUMERS) a.dst[x - a.w0] = fe_header_char<MODE>(H, (int)(x - O));
             }
-            const int64_t s1 = O + h + pc.len;
+            const int64_t s0 = O + h, s1 = s0 + pc.len;
             if (ct == 0 && s1 >= x0 && s1 < x1) a.dst[s1 - a.w0] = '\n';
             if (pc.n > 0) {
-                uint8_t* d = a.dst + (pc.p0 - a.w0);
+                uint8_t* d = a.dst + ((s0 > x0 ? s0 : x0) - a.w0);
                 consumers_copy_from_smem(d, s.stage[slot] + pc.soff, pc.n_stage, ct);
                 for (int q = pc.n_stage + ct; q < pc.n; q += FE_CONSUMERS) d[q] = pc.src[q]; // arena tail not covered by the bulk copy
             }
+            if (hv) a.dst[hp0 + ct - a.w0] = hc;
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&s.empty[slot]); // this warp no longer reads the slot
@@ -527,8 +564,13 @@ void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
     if (a.w1 <= a.w0 || a.G <= 0) return;
     int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
     int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
-    cudaFuncSetAttribute(k_fasta_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
-    k_fasta_emit<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
+        kern<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);
+    };
+    if (a.split_len > 0) go(k_fasta_emit<2>);
+    else if (a.sim) go(k_fasta_emit<1>);
+    else go(k_fasta_emit<0>);
 }
 
 __global__ void k_sample_i64(const int64_t* __restrict__ src, int64_t n, int step, int64_t cnt, int64_t* dst)
