@@ -17,10 +17,11 @@ __device__ __forceinline__ bool add_interval(int32_t* diff, const int64_t* __res
 {
     int64_t base = slot_off[lr];
     int64_t nb = slot_off[lr + 1] - base - 1;
-    int64_t lo = (int64_t)(s < 0 ? 0 : s) / reso;
+    // s, e are 32-bit and reso >= 1: both quotients fit 32-bit unsigned division
+    int64_t lo = (int64_t)((unsigned)(s < 0 ? 0 : s) / (unsigned)reso);
     int64_t em = (int64_t)e - 1;
     if (em < lo * reso) return true; // nothing covered (repeat.hpp:69 never true)
-    int64_t hi = em / reso;
+    int64_t hi = (int64_t)((unsigned)em / (unsigned)reso); // 0 <= lo*reso <= em < 2^31 here
     if (hi >= nb) return false;
     atomicAdd(diff + base + lo, 1);
     atomicAdd(diff + base + hi + 1, -1);

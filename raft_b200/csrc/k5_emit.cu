@@ -158,8 +158,8 @@ void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream
     a.text_cap = CE_CAP;
     if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CE_CAP) a.text_cap = v; } // test knob: force the direct path
     cudaFuncSetAttribute(k_cov_text<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
-    const int64_t per_sm = a.ctas_per_sm > 0 ? a.ctas_per_sm : 6;
-    const int64_t grid = n_tiles_launch < 148 * per_sm ? n_tiles_launch : 148 * per_sm;
+    // ctas_per_sm == 0: one CTA per tile (the loop in the kernel runs once)
+    const int64_t grid = a.ctas_per_sm > 0 && n_tiles_launch > 148 * (int64_t)a.ctas_per_sm ? 148 * (int64_t)a.ctas_per_sm : n_tiles_launch;
     k_cov_text<true><<<(unsigned)grid, CE_THREADS, CE_SMEM, st>>>(a, n_tiles_launch);
 }
 

@@ -187,7 +187,7 @@ struct CovEmitArgs {
     int64_t        tile_first; // first tile of this launch
     const int32_t* tile_read;  // n_tiles+1: read containing the tile's first slot (last entry = m-1 sentinel)
     int            text_cap;   // tiles with more text than this take the direct (byte-wise) path
-    int            ctas_per_sm; // persistent grid = 148 x this (0: default 6; 2 when sharing the GPU with the gather)
+    int            ctas_per_sm; // > 0: persistent grid of 148 x this; 0: one CTA per tile
 };
 // tile_read[T] = read whose slots contain slot T*COV_TILE_SLOTS
 void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, int32_t* tile_read, cudaStream_t st);
