@@ -103,7 +103,7 @@ struct raftgpu_ctx {
     DevBuf  b_cov; bool diff_zeroed = false, finalized = false, sized = false;
     DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
-    DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
+    DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_static, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
     std::vector<int64_t> h_cov_tile_off, h_rep_line_off; // every OFF_SAMPLE-th entry of the device tables (+ the last)
     DevBuf  b_off_sample, b_sim, b_bed_line_size, b_bed_line_off;
     std::vector<int64_t> h_bed_line_off;
@@ -371,7 +371,10 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
         const int T = cov_tiles(tot[0]);
         CK(ctx->b_cov_tile_read.ensure(sizeof(int32_t) * (size_t)(T + 2)));
         CK(ctx->b_cov_tile_bytes.ensure(sizeof(int32_t) * (size_t)(T + 1)));
+        CK(ctx->b_cov_tile_static.ensure(sizeof(int32_t) * (size_t)(T + 1)));
         launch_cov_tile_index(ctx->b_slot_off.as<int64_t>(), m, tot[0], ctx->b_cov_tile_read.as<int32_t>(), ctx->st);
+        CKL();
+        launch_cov_static_sizes(ctx->b_slot_off.as<int64_t>(), m, tot[0], ctx->own_first, P.reso, ctx->b_cov_tile_static.as<int32_t>(), ctx->st);
         CKL();
     }
     CK(cudaMemcpyAsync(&tot[1], ctx->b_rep_cap_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -467,10 +470,8 @@ extern "C" int raftgpu_set_reads_sharded(raftgpu_ctx* ctx, int64_t n, const int6
         if (own_count) CK(cudaMemcpy(len.data(), lengths + own_first, sizeof(int64_t) * own_count, cudaMemcpyDefault));
         for (int64_t i = 0; i < own_count; i++) off[i + 1] = off[i] + len[i];
         seq_bytes = off[own_count];
-        const int64_t* tmp = nullptr;
         CK(ctx->b_seq_off.ensure(sizeof(int64_t) * (own_count + 1) + 32));
         CK(cudaMemcpy(ctx->b_seq_off.p, off.data(), sizeof(int64_t) * (own_count + 1), cudaMemcpyHostToDevice));
-        (void)tmp;
         ctx->d_seq_off = ctx->b_seq_off.as<int64_t>();
     }
     ctx->have_seq = own_seq != nullptr || seq_bytes == 0;
@@ -885,7 +886,7 @@ extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
     // K2b: coverage = inclusive scan of the difference array
     cudaEventRecord(ctx->ev[3], ctx->st);
     CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_cov(ctx->n_slots) + scan_tiles_small(std::max<int64_t>(m, ctx->cut_cap_total + m)) + 16)));
-    CovSizeArgs cs{ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_slot_off.as<int64_t>(), ctx->b_cov_tile_read.as<int32_t>(), ctx->own_first, P.reso};
+    CovSizeArgs cs{ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_static.as<int32_t>()};
     launch_scan_cov_inplace(ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, cs, ctx->st);
     CKL();
     cudaEventRecord(ctx->ev[4], ctx->st);

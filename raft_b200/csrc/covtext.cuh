@@ -1,4 +1,4 @@
-// covtext.cuh — slot walk and text sizing of coverage.txt, shared by the scan (fused sizing) and the emitter.
+// covtext.cuh — slot walk and per-slot digit counts of coverage.txt (emitter K5a).
 // coverage.txt (repeat.hpp:105-108): "read " i " " then k*reso "," cov " " per bin, then "\n".
 #pragma once
 #include "kernels.h"
@@ -43,27 +43,5 @@ __device__ __forceinline__ int slot_digits(int bin, int reso, int cov)
     return dec_digits((uint32_t)bin * (uint32_t)reso) | (dec_digits(ucov) << 4) | ((cov < 0) << 8);
 }
 
-
-// bytes of coverage.txt contributed by `cnt` (<= 4) consecutive slots starting at global slot g with coverages cv[]
-__device__ __forceinline__ int cov_text_size4(const int64_t* __restrict__ slot_off, const int32_t* __restrict__ tile_read, int64_t g, int cnt,
-                                              const int* cv, int reso, int64_t own_first)
-{
-    const int64_t ct = g / COV_TILE_SLOTS;
-    int64_t       lo = tile_read[ct], hi = (int64_t)tile_read[ct + 1] + 1;
-    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (slot_off[mid] <= g) lo = mid; else hi = mid; }
-    SlotWalk w;
-    w.init(slot_off, lo, g);
-    int sz = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (k < cnt) {
-            if (w.bin == 0) sz += 5 + dec_digits64((uint64_t)(own_first + w.r)) + 1;
-            if (w.left == 1) sz += 1;
-            else { int d = slot_digits(w.bin, reso, cv[k]); sz += (d & 15) + ((d >> 4) & 15) + (d >> 8) + 2; }
-            w.next();
-        }
-    }
-    return sz;
-}
 
 } // namespace raftk

@@ -87,8 +87,50 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ROUNDS = 4;
 constexpr int CS_TILE = CS_THREADS * 4 * CS_ROUNDS; // 4096 ints = 16 KiB
 
+// Sum over bins b in [b0, b1) of the decimal length of b*reso (b*reso < 2^31): every bin has one digit, and one more
+// for every power of ten it reaches.
+__device__ __forceinline__ int64_t pos_digit_sum(int64_t b0, int64_t b1, int reso)
+{
+    int64_t sum = b1 - b0, p = 10;
+    for (int d = 1; d <= 9; d++, p *= 10) {
+        const int64_t thr = (p + reso - 1) / reso; // first bin with b*reso >= 10^d
+        if (thr >= b1) break;
+        sum += b1 - (b0 > thr ? b0 : thr);
+    }
+    return sum;
+}
+__global__ void __launch_bounds__(256) k_cov_static(const int64_t* __restrict__ slot_off, int64_t m, int64_t own_first, int reso, int32_t* tile_static)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t s0 = slot_off[i], s1 = slot_off[i + 1]; // bins s0 .. s1-2, sentinel s1-1
+    const int     pre = 5 + dec_digits64((uint64_t)(own_first + i)) + 1;
+    for (int64_t T = s0 / COV_TILE_SLOTS; T * COV_TILE_SLOTS < s1; T++) {
+        const int64_t lo = T * COV_TILE_SLOTS > s0 ? T * COV_TILE_SLOTS : s0;
+        const int64_t hi = (T + 1) * COV_TILE_SLOTS < s1 ? (T + 1) * COV_TILE_SLOTS : s1;
+        const int64_t b1 = (hi < s1 ? hi : s1 - 1) - s0;
+        int64_t       sz = b1 > lo - s0 ? pos_digit_sum(lo - s0, b1, reso) : 0;
+        if (lo == s0) sz += pre;
+        if (hi == s1) sz -= 2; // the sentinel is one newline; the scan counts digits(0) + 2 for it
+        atomicAdd(tile_static + T, (int32_t)sz);
+    }
+}
+void launch_cov_static_sizes(const int64_t* slot_off, int64_t m, int64_t n_slots, int64_t own_first, int reso, int32_t* tile_static, cudaStream_t st)
+{
+    const int64_t T = (n_slots + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS;
+    if (T <= 0 || m <= 0) return;
+    cudaMemsetAsync(tile_static, 0, sizeof(int32_t) * (size_t)T, st);
+    k_cov_static<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(slot_off, m, own_first, reso, tile_static);
+}
+
 // The scan is memory-bound with most issue slots idle, so it also sizes coverage.txt: every thread knows the final
-// coverage of its 16 slots and adds their text bytes into the 1024-slot tile counters the emitter (K5a) uses.
+// coverage of its 16 slots and adds digits(cov) + 2 per slot into the 1024-slot tile counters the emitter (K5a) uses
+// (the counters start from the coverage-independent part, launch_cov_static_sizes).
+__device__ __forceinline__ int cov_dyn_bytes(int c)
+{
+    const unsigned u = c < 0 ? (unsigned)(-(int64_t)c) : (unsigned)c;
+    return (u < 100u ? (u < 10u ? 3 : 4) : dec_digits(u) + 2) + (c < 0);
+}
 __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ data, int64_t n, uint64_t* status, int* ticket, CovSizeArgs cs)
 {
     __shared__ int      ws[34];
@@ -133,9 +175,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
         int     a = p0 + lane_ex[r];
         int4    o;
         o.x = a + v[r].x; o.y = o.x + v[r].y; o.z = o.y + v[r].z; o.w = o.z + v[r].w;
-        if (cs.tile_bytes && i < n) {
-            const int cvv[4] = {o.x, o.y, o.z, o.w};
-            text_bytes += cov_text_size4(cs.slot_off, cs.tile_read, i, (n - i) < 4 ? (int)(n - i) : 4, cvv, cs.reso, cs.own_first);
+        if (cs.tile_bytes) {
+            if (full) text_bytes += cov_dyn_bytes(o.x) + cov_dyn_bytes(o.y) + cov_dyn_bytes(o.z) + cov_dyn_bytes(o.w);
+            else text_bytes += (i + 0 < n ? cov_dyn_bytes(o.x) : 0) + (i + 1 < n ? cov_dyn_bytes(o.y) : 0) +
+                               (i + 2 < n ? cov_dyn_bytes(o.z) : 0) + (i + 3 < n ? cov_dyn_bytes(o.w) : 0);
         }
         if (full) {
             *reinterpret_cast<int4*>(data + i) = o;
@@ -156,7 +199,8 @@ void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ti
     if (tiles == 0) return;
     cudaMemsetAsync(status, 0, sizeof(uint64_t) * tiles, st);
     cudaMemsetAsync(ticket, 0, sizeof(int), st);
-    if (cs.tile_bytes) cudaMemsetAsync(cs.tile_bytes, 0, sizeof(int32_t) * (size_t)((n + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS), st);
+    if (cs.tile_bytes)
+        cudaMemcpyAsync(cs.tile_bytes, cs.tile_static, sizeof(int32_t) * (size_t)((n + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS), cudaMemcpyDeviceToDevice, st);
     k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(data, n, status, ticket, cs);
 }
 
@@ -233,11 +277,11 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
         if (!sym && t != q && (t < own_lo || t >= own_hi)) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
     }
     __syncthreads();
-    if (!PACK) {
+    if constexpr (!PACK) {
         for (int r = threadIdx.x; r < nranks; r += blockDim.x)
             if (s_cnt[r]) atomicAdd(&counters[r], s_cnt[r]);
         return;
-    }
+    } else {
     // pass 2: reserve a range per destination, then write
     for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
         s_cnt[nranks + r] = s_cnt[r] ? atomicAdd(&counters[r], s_cnt[r]) : 0ull;
@@ -256,6 +300,7 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
             unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
             sendbuf[3 * slot] = t; sendbuf[3 * slot + 1] = a.ts[k]; sendbuf[3 * slot + 2] = a.te[k];
         }
+    }
     }
 }
 static unsigned route_blocks(int64_t n) { int64_t b = (n + 4095) / 4096; if (b < 1) b = 1; if (b > 148 * 8) b = 148 * 8; return (unsigned)b; }

@@ -80,12 +80,13 @@ void launch_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, uint64_t
 // in-place inclusive scan of the int32 difference array, fused with the sizing of coverage.txt (bytes per 1024-slot tile)
 constexpr int COV_TILE_SLOTS = 1024;
 struct CovSizeArgs {
-    int32_t*       tile_bytes; // null: scan only
-    const int64_t* slot_off;
-    const int32_t* tile_read;
-    int64_t        own_first;
-    int            reso;
+    int32_t*       tile_bytes;  // null: scan only
+    const int32_t* tile_static; // coverage-independent bytes of every tile (launch_cov_static_sizes); tile_bytes starts from it
 };
+// Coverage-independent part of coverage.txt per 1024-slot tile: "read i " prefixes, the digits of every bin position
+// (closed form per read and tile) and the sentinel newline, minus the 3 bytes the scan counts for a sentinel (whose
+// coverage is always 0).  The scan then only adds digits(cov) + 2 per slot.
+void launch_cov_static_sizes(const int64_t* slot_off, int64_t m, int64_t n_slots, int64_t own_first, int reso, int32_t* tile_static, cudaStream_t st);
 int  scan_tiles_cov(int64_t n);
 void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st);
 
