@@ -17,7 +17,7 @@ $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh 
 
 $(OBJ)/host_io.o: $(SRC)/host_io.cpp include/raft_b200.h
 	@mkdir -p $(OBJ)
-	$(CXX) -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz

@@ -206,6 +206,11 @@ int raftgpu_set_output_base(raftgpu_ctx *ctx, int64_t first_read_num);
  * long_repeats.bed,reads.fasta}, and prints the reference's stdout lines. */
 int raftgpu_break_long_reads(const char *readfilename, const char *paffilename, const raftgpu_params *p,
                              const char *prefix, int device, raftgpu_stats *stats);
+/* Same with several PAF files read back to back, as `cat a.paf b.paf` would feed them (README.md:32-38:
+ * hifiasm writes <prefix>.0.ovlp.paf and <prefix>.1.ovlp.paf); gzip or plain, streamed through two pinned
+ * buffers by a reader thread so file reading overlaps the device tokenizer.  n_paf >= 1. */
+int raftgpu_break_long_reads_multi(const char *readfilename, int n_paf, const char *const *paffilenames,
+                                   const raftgpu_params *p, const char *prefix, int device, raftgpu_stats *stats_out);
 
 #ifdef __cplusplus
 }

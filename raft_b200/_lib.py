@@ -14,6 +14,7 @@ SYMBOLS = [
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
     "raftgpu_accumulate_local", "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
+    "raftgpu_break_long_reads_multi",
 ]
 
 
@@ -84,6 +85,7 @@ def lib():
         "raftgpu_finalize": (C.c_int, [vp, PS]),
         "raftgpu_set_output_base": (C.c_int, [vp, i64]),
         "raftgpu_break_long_reads": (C.c_int, [C.c_char_p, C.c_char_p, PP, C.c_char_p, C.c_int, PS]),
+        "raftgpu_break_long_reads_multi": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), PP, C.c_char_p, C.c_int, PS]),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)  # AttributeError if the symbol is not exported

@@ -248,12 +248,17 @@ def load_fasta(path):
     return seq_off, seq, name_off, names
 
 
-def break_long_reads(readfilename: str, paffilename: str, params: AlgoParams, device: int = 0):
-    """Drop-in for break_long_reads (chop.hpp:331-373): files in, prefix.* files out."""
+def break_long_reads(readfilename: str, paffilename, params: AlgoParams, device: int = 0):
+    """Drop-in for break_long_reads (chop.hpp:331-373): files in, prefix.* files out.
+
+    `paffilename` may be a list of paths: they are ingested back to back as `cat` would join them
+    (README.md:35-36 merges hifiasm's *.0.ovlp.paf and *.1.ovlp.paf before calling raft)."""
     L = _lib.lib()
     s = _lib.Stats()
-    st = L.raftgpu_break_long_reads(readfilename.encode(), paffilename.encode(), C.byref(params.c_struct()),
-                                    params.outputfilename.encode(), device, C.byref(s))
+    pafs = [paffilename] if isinstance(paffilename, (str, bytes)) else list(paffilename)
+    arr = (C.c_char_p * len(pafs))(*[q.encode() if isinstance(q, str) else q for q in pafs])
+    st = L.raftgpu_break_long_reads_multi(readfilename.encode(), len(pafs), arr, C.byref(params.c_struct()),
+                                          params.outputfilename.encode(), device, C.byref(s))
     if st:
         raise RaftError(st)
     return s

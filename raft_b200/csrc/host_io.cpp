@@ -1,9 +1,13 @@
 // host_io.cpp — host side of the boundary: FASTA/FASTQ(+gz) reader and the file-level drop-in for
 // break_long_reads (chop.hpp:331-373).  No compute here: everything numeric happens on the device
 // through the C ABI in include/raft_b200.h.
+#include <cuda_runtime.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include <cctype>
 #include <cstdio>
@@ -138,6 +142,95 @@ T* steal(const std::vector<T>& v)
     return p;
 }
 
+// Sequential byte source over several files (gzip or plain), read by a background thread into two pinned buffers.
+class PafPipeline {
+public:
+    PafPipeline(const char* const* paths, int n) : paths_(paths, paths + n)
+    {
+        for (int k = 0; k < 2; k++) {
+            void* p = nullptr;
+            if (cudaHostAlloc(&p, CAP, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = malloc(CAP); pinned_[k] = false; }
+            buf_[k] = (uint8_t*)p;
+        }
+        th_ = std::thread([this] { run(); });
+    }
+    ~PafPipeline()
+    {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+        for (int k = 0; k < 2; k++) if (buf_[k]) { if (pinned_[k]) cudaFreeHost(buf_[k]); else free(buf_[k]); }
+    }
+    // next filled buffer; false on a read error
+    bool next(const uint8_t** data, size_t* fill, bool* last)
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [&] { return state_[cons_] == FULL || error_; });
+        if (error_) return false;
+        *data = buf_[cons_]; *fill = fill_[cons_]; *last = last_[cons_];
+        return true;
+    }
+    void release()
+    {
+        { std::lock_guard<std::mutex> g(mu_); state_[cons_] = EMPTY; cons_ ^= 1; }
+        cv_.notify_all();
+    }
+
+private:
+    static constexpr size_t CAP = 256u << 20;
+    enum { EMPTY, FULL };
+    void run()
+    {
+        size_t file = 0;
+        gzFile gz = nullptr;
+        int    k = 0;
+        bool   done = false;
+        while (!done) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return state_[k] == EMPTY || stop_; });
+                if (stop_) break;
+            }
+            size_t fill = 0;
+            while (fill < CAP && !done) {
+                if (!gz) {
+                    if (file == paths_.size()) { done = true; break; }
+                    gz = gzopen(paths_[file++], "r"); // transparent for plain files, like the reference (paf.hpp:29)
+                    if (!gz) { fail(); return; }
+                    gzbuffer(gz, 4 << 20);
+                }
+                int got = gzread(gz, buf_[k] + fill, (unsigned)std::min<size_t>(CAP - fill, 1u << 30));
+                if (got < 0) { gzclose(gz); fail(); return; }
+                if (got == 0) { gzclose(gz); gz = nullptr; continue; }
+                fill += (size_t)got;
+            }
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                fill_[k] = fill; last_[k] = done; state_[k] = FULL;
+            }
+            cv_.notify_all();
+            k ^= 1;
+        }
+        if (gz) gzclose(gz);
+    }
+    void fail()
+    {
+        { std::lock_guard<std::mutex> g(mu_); error_ = true; }
+        cv_.notify_all();
+    }
+    std::vector<const char*> paths_;
+    uint8_t*                 buf_[2] = {nullptr, nullptr};
+    bool                     pinned_[2] = {true, true};
+    size_t                   fill_[2] = {0, 0};
+    bool                     last_[2] = {false, false};
+    int                      state_[2] = {EMPTY, EMPTY};
+    int                      cons_ = 0;
+    bool                     stop_ = false, error_ = false;
+    std::mutex               mu_;
+    std::condition_variable  cv_;
+    std::thread              th_;
+};
+
 bool file_missing_or_empty(const char* fn)
 { // chop.hpp:326-349
     std::ifstream f(fn);
@@ -191,17 +284,25 @@ static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, s
 extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* paffilename, const raftgpu_params* p, const char* prefix,
                                         int device, raftgpu_stats* stats_out)
 {
-    if (!readfilename || !paffilename || !p || !prefix) return RAFTGPU_E_ARG;
+    return raftgpu_break_long_reads_multi(readfilename, 1, &paffilename, p, prefix, device, stats_out);
+}
+
+extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_paf, const char* const* paffilenames, const raftgpu_params* p,
+                                              const char* prefix, int device, raftgpu_stats* stats_out)
+{
+    if (!readfilename || n_paf < 1 || !paffilenames || !p || !prefix) return RAFTGPU_E_ARG;
+    for (int k = 0; k < n_paf; k++) if (!paffilenames[k]) return RAFTGPU_E_ARG;
     const std::string pre(prefix);
     { std::ofstream touch(pre + ".reads.fasta"); } // chop.hpp:333: created before the inputs are validated
     if (file_missing_or_empty(readfilename)) {
         printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", readfilename);
         return RAFTGPU_E_IO;
     }
-    if (file_missing_or_empty(paffilename)) {
-        printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", paffilename);
-        return RAFTGPU_E_IO;
-    }
+    for (int k = 0; k < n_paf; k++)
+        if (file_missing_or_empty(paffilenames[k])) {
+            printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", paffilenames[k]);
+            return RAFTGPU_E_IO;
+        }
     raftgpu_ctx* ctx = nullptr;
     int          st = raftgpu_create(p, device, &ctx);
     if (st) { fprintf(stderr, "raft_b200: %s\n", raftgpu_strerror(st)); return st; }
@@ -248,24 +349,22 @@ extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* pa
         if (st) return fail(st);
     }
 
-    // PAF: inflate (or read) in chunks and hand them to the tokenizer (paf.hpp:24-38 uses gzopen/gzread too)
+    // PAF: one reader thread inflates (gz, paf.hpp:24-38) or reads (plain) the files back to back into two pinned
+    // buffers while this thread hands the other buffer to the tokenizer, so disk/zlib time overlaps H2D + parse and
+    // only the decoded records (28 B each) stay on the device: the text itself may exceed HBM.  Several files behave
+    // like `cat a b | raft ...` (README.md:32-38: hifiasm writes two *.ovlp.paf files).
     {
-        gzFile fp = gzopen(paffilename, "r");
-        if (!fp) return fail(RAFTGPU_E_IO);
-        gzbuffer(fp, 1 << 20);
-        std::vector<uint8_t> buf(256u << 20);
+        PafPipeline pipe(paffilenames, n_paf);
         for (;;) {
-            size_t fill = 0;
-            while (fill < buf.size()) {
-                int got = gzread(fp, buf.data() + fill, (unsigned)std::min<size_t>(buf.size() - fill, 1u << 30));
-                if (got <= 0) break;
-                fill += (size_t)got;
-            }
-            bool last = fill < buf.size();
-            if ((st = raftgpu_ingest_paf(ctx, buf.data(), fill, last ? 1 : 0))) { gzclose(fp); return fail(st); }
+            const uint8_t* data = nullptr;
+            size_t         fill = 0;
+            bool           last = false;
+            if (!pipe.next(&data, &fill, &last)) return fail(RAFTGPU_E_IO);
+            st = raftgpu_ingest_paf(ctx, data, fill, last ? 1 : 0);
+            pipe.release();
+            if (st) return fail(st);
             if (last) break;
         }
-        gzclose(fp);
     }
     if ((st = raftgpu_run(ctx, &s))) {
         // the reference prints these before it would have crashed; keep stdout comparable up to the failure

@@ -66,7 +66,10 @@ int main(int argc, char* argv[])
     std::cout.flush();
 
     const char* dev_env = getenv("RAFT_B200_DEVICE");
-    int         st = raftgpu_break_long_reads(argv[optind], argv[optind + 1], &p, prefix.c_str(), dev_env ? atoi(dev_env) : 0, nullptr);
+    // extension over main.cpp:75 (whose third positional argument is unused): any further positional arguments are
+    // more PAF files, ingested back to back as `cat` would join them (README.md:35-36 merges hifiasm's two files)
+    int         st = raftgpu_break_long_reads_multi(argv[optind], argc - optind - 1, argv + optind + 1, &p, prefix.c_str(),
+                                                    dev_env ? atoi(dev_env) : 0, nullptr);
     fflush(stdout);
     if (st == RAFTGPU_E_IO) return 1; // chop.hpp:339-348 exit(1)
     if (st != RAFTGPU_OK) return 2;   // inputs on which the reference crashes (segfault / SIGFPE / throw) or CUDA failure

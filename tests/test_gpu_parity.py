@@ -186,6 +186,60 @@ def test_cli_binary_against_golden():
             assert got == entry["stdout"], entry["name"]
 
 
+def test_cli_two_paf_files_equal_cat():
+    """f4(ii): several PAF files (plain, cut mid-line, + gzip) are ingested back to back like `cat a b` (README.md:35-36)."""
+    import gzip
+    exe = os.path.join(ROOT, "raft_b200", "raft")
+    entry = max(CASES, key=lambda e: len(load_inputs(e)[1]))
+    fa, paf = load_inputs(entry)
+    cut = len(paf) // 2 + 7          # not on a line boundary: the tail of the first file joins the head of the second
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "r.fa"), "wb").write(fa)
+        open(os.path.join(d, "a.paf"), "wb").write(paf[:cut])
+        with gzip.open(os.path.join(d, "b.paf.gz"), "wb") as f:
+            f.write(paf[cut:])
+        r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "out"), os.path.join(d, "r.fa"), os.path.join(d, "a.paf"),
+                                                    os.path.join(d, "b.paf.gz")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+        assert r.returncode == 0, r.stdout.decode()
+        for suf in SUFS:
+            check_output(entry, suf, open(os.path.join(d, "out." + suf), "rb").read())
+        got = [l for l in r.stdout.decode().splitlines() if not l.startswith("INFO, main(), program completed") and "CMD:" not in l]
+        assert got == entry["stdout"], entry["name"]
+        # python mirror, list form
+        p = api.AlgoParams.from_args(entry["args"] + ["-o", os.path.join(d, "py")])
+        api.break_long_reads(os.path.join(d, "r.fa"), [os.path.join(d, "a.paf"), os.path.join(d, "b.paf.gz")], p)
+        for suf in SUFS:
+            check_output(entry, suf, open(os.path.join(d, "py." + suf), "rb").read())
+        # a missing second file is reported like a missing first one (chop.hpp:344-348)
+        r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "o2"), os.path.join(d, "r.fa"), os.path.join(d, "a.paf"),
+                                                    os.path.join(d, "nope.paf")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+        assert r.returncode == 1 and b"nope.paf input file either does not exist or is empty" in r.stdout
+
+
+def test_async_fetch_lanes():
+    """raftgpu_fetch_async queues emitters on the two emit lanes (text outputs / sequence outputs); raftgpu_sync joins them."""
+    torch = pytest.importorskip("torch")
+    ds = synth.make_dataset("C1", 0.2, True, seed=12)
+    p = api.AlgoParams.from_args(ds.args)
+    ctx, st = gpu_run(ds.reads, ds.paf, p)
+    ref = O.run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)))
+    dev = torch.device("cuda:0")
+    want = {api.OUT_COVERAGE: ref.cov_txt, api.OUT_LONG_REPEATS: ref.rep_txt, api.OUT_READS_FASTA: ref.fasta}
+    bufs = {w: torch.zeros(len(d) + 16, dtype=torch.uint8, device=dev) for w, d in want.items()}
+    torch.cuda.synchronize()
+    # interleave windows of the three streams without waiting in between
+    for lo_frac, hi_frac in ((0.0, 0.37), (0.37, 1.0)):
+        for w, d in want.items():
+            lo, hi = int(len(d) * lo_frac), int(len(d) * hi_frac)
+            if hi > lo:
+                ctx.fetch_async(w, lo, bufs[w][lo:], hi - lo)
+    ctx.sync()
+    for w, d in want.items():
+        assert bufs[w][:len(d)].cpu().numpy().tobytes() == d, w
+        assert int(bufs[w][len(d):].sum()) == 0
+    ctx.close()
+
+
 def _stress_paf(ds, seed=0):
     """PAF text with everything the tokenizer's mask logic can trip on: lines longer than the staged
     overhang (kilobyte tags), lines crossing 16 KiB tile boundaries, blank-line runs, short lines,
