@@ -143,9 +143,9 @@ T* steal(const std::vector<T>& v)
 }
 
 // Sequential byte source over several files (gzip or plain), read by a background thread into two pinned buffers.
-class PafPipeline {
+class FilePipeline {
 public:
-    PafPipeline(const char* const* paths, int n) : paths_(paths, paths + n)
+    FilePipeline(const char* const* paths, int n) : paths_(paths, paths + n)
     {
         for (int k = 0; k < 2; k++) {
             void* p = nullptr;
@@ -154,7 +154,7 @@ public:
         }
         th_ = std::thread([this] { run(); });
     }
-    ~PafPipeline()
+    ~FilePipeline()
     {
         { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
         cv_.notify_all();
@@ -263,22 +263,65 @@ extern "C" int raftgpu_load_fasta(const char* path, int64_t* n, int64_t** seq_of
     return RAFTGPU_OK;
 }
 
+// Writes one output stream to `path`: this thread fetches 256 MiB windows into two pinned buffers (D2H through the
+// C ABI) while a writer thread drains the other buffer to the file.
 static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, std::string& err)
 {
     uint64_t total = 0;
     if (raftgpu_output_size(ctx, which, &total)) { err = raftgpu_last_error(ctx); return false; }
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) { err = "cannot open " + path; return false; }
-    const size_t         W = 512u << 20;
-    std::vector<uint8_t> buf((size_t)std::min<uint64_t>(W, total ? total : 1));
-    for (uint64_t off = 0; off < total; off += W) {
-        size_t len = (size_t)std::min<uint64_t>(W, total - off);
-        int    st = raftgpu_fetch(ctx, which, off, buf.data(), len);
-        if (st) { err = std::string(raftgpu_strerror(st)) + ": " + raftgpu_last_error(ctx); fclose(f); return false; }
-        if (fwrite(buf.data(), 1, len, f) != len) { err = "short write to " + path; fclose(f); return false; }
+    const size_t W = (size_t)std::min<uint64_t>(256u << 20, total ? total : 1);
+    uint8_t*     buf[2] = {nullptr, nullptr};
+    bool         pinned[2] = {true, true};
+    for (int k = 0; k < 2; k++) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, W, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = malloc(W); pinned[k] = false; }
+        buf[k] = (uint8_t*)p;
     }
-    fclose(f);
-    return true;
+    std::mutex              mu;
+    std::condition_variable cv;
+    size_t                  len[2] = {0, 0};
+    bool                    full[2] = {false, false}, done = false, werr = false;
+    std::thread writer([&] {
+        for (int k = 0;; k ^= 1) {
+            std::unique_lock<std::mutex> g(mu);
+            cv.wait(g, [&] { return full[k] || done; });
+            if (!full[k]) return;
+            g.unlock();
+            if (!werr && fwrite(buf[k], 1, len[k], f) != len[k]) werr = true;
+            g.lock();
+            full[k] = false;
+            cv.notify_all();
+        }
+    });
+    bool ok = true;
+    int  k = 0;
+    for (uint64_t off = 0; off < total && ok; off += W, k ^= 1) {
+        {
+            std::unique_lock<std::mutex> g(mu);
+            cv.wait(g, [&] { return !full[k]; });
+        }
+        const size_t n = (size_t)std::min<uint64_t>(W, total - off);
+        const int    st = raftgpu_fetch(ctx, which, off, buf[k], n);
+        if (st) { err = std::string(raftgpu_strerror(st)) + ": " + raftgpu_last_error(ctx); ok = false; break; }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            len[k] = n; full[k] = true;
+        }
+        cv.notify_all();
+    }
+    {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return !full[0] && !full[1]; });
+        done = true;
+    }
+    cv.notify_all();
+    writer.join();
+    for (int q = 0; q < 2; q++) if (buf[q]) { if (pinned[q]) cudaFreeHost(buf[q]); else free(buf[q]); }
+    if (fclose(f) != 0) werr = true;
+    if (werr && ok) { err = "short write to " + path; ok = false; }
+    return ok;
 }
 
 extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* paffilename, const raftgpu_params* p, const char* prefix,
@@ -322,15 +365,15 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
         if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
             fseeko(f, 0, SEEK_END);
             const uint64_t fsize = (uint64_t)ftello(f);
-            fseeko(f, 0, SEEK_SET);
-            std::vector<uint8_t> buf(std::min<uint64_t>(256u << 20, fsize ? fsize : 1));
-            uint64_t done = 0;
+            FilePipeline   pipe(&readfilename, 1); // reader thread + two pinned buffers, like the PAF below
             st = RAFTGPU_OK;
             while (st == RAFTGPU_OK) {
-                size_t r = fread(buf.data(), 1, buf.size(), f);
-                done += r;
-                const bool last = done >= fsize || r == 0;
-                st = raftgpu_ingest_fasta(ctx, buf.data(), r, last ? 1 : 0, fsize);
+                const uint8_t* data = nullptr;
+                size_t         fill = 0;
+                bool           last = false;
+                if (!pipe.next(&data, &fill, &last)) { fclose(f); return fail(RAFTGPU_E_IO); }
+                st = raftgpu_ingest_fasta(ctx, data, fill, last ? 1 : 0, fsize);
+                pipe.release();
                 if (last) break;
             }
             if (st == RAFTGPU_OK) on_device = true;
@@ -354,7 +397,7 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
     // only the decoded records (28 B each) stay on the device: the text itself may exceed HBM.  Several files behave
     // like `cat a b | raft ...` (README.md:32-38: hifiasm writes two *.ovlp.paf files).
     {
-        PafPipeline pipe(paffilenames, n_paf);
+        FilePipeline pipe(paffilenames, n_paf);
         for (;;) {
             const uint8_t* data = nullptr;
             size_t         fill = 0;
