@@ -219,15 +219,11 @@ int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
     raftgpu_ctx* ctx = new raftgpu_ctx();
     ctx->device = device; ctx->prm = *p;
     auto bail = [&](void) { delete ctx; return RAFTGPU_E_CUDA; };
-    // the main stream (which also carries the HBM-bound reads.fasta gather) outranks the text-emit lane: gather CTAs
-    // are placed first whenever SM resources free up, the coverage.txt emitter fills what is left
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) return bail();
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
-    if (cudaStreamCreateWithPriority(&ctx->st_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess) return bail();
     ctx->lane[0].st = ctx->st_aux; ctx->lane[1].st = ctx->st;
     for (auto& L : ctx->lane) if (cudaEventCreate(&L.ev0) != cudaSuccess || cudaEventCreate(&L.ev1) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking) != cudaSuccess) return bail();

@@ -263,11 +263,11 @@ void launch_bed_emit(const RepEmitArgs& a, cudaStream_t st)
 // starts in the tile also fetches the name extent, so the consumers never chase name_off.  Warps 1..7 are
 // consumers: they wait on the slot's `full` mbarrier (producer arrive + TMA transaction bytes), generate the
 // few header bytes, realign the staged bases (two aligned 128-bit shared loads + funnel shifts) into aligned
-// 128-bit streaming stores, and release the slot through its `empty` mbarrier.  With n slots, n-1 tiles of
-// loads are in flight per CTA behind the tile being stored.
+// 128-bit streaming stores, and release the slot through its `empty` mbarrier.  Three slots keep two tiles
+// of loads in flight per CTA behind the tile being stored.
 constexpr int FE_THREADS = 256;
 constexpr int FE_CONSUMERS = FE_THREADS - 32;       // 7 warps
-constexpr int FE_MAX_SLOTS = 6;
+constexpr int FE_SLOTS = 3;
 constexpr int FE_MAXP = 32;                         // pieces per slot (one producer round)
 constexpr int FE_STAGE = FASTA_TILE + 512;          // staged source bytes per slot (alignment slack; overflow spills to the next slot)
 
@@ -285,21 +285,14 @@ struct FePiece {
 };
 static_assert(sizeof(FePiece) == 64, "FePiece layout");
 
-// dynamic shared memory: control block, then nslots stage buffers, then nslots piece lists
-struct __align__(16) FeCtl {
-    long long x0[FE_MAX_SLOTS], x1[FE_MAX_SLOTS];
-    uint64_t  full[FE_MAX_SLOTS], empty[FE_MAX_SLOTS];
-    int       np[FE_MAX_SLOTS]; // -1: no more work
+struct __align__(16) FeSmem {
+    uint8_t   stage[FE_SLOTS][FE_STAGE];
+    FePiece   piece[FE_SLOTS][FE_MAXP];
+    long long x0[FE_SLOTS], x1[FE_SLOTS];
+    int       np[FE_SLOTS]; // -1: no more work
+    uint64_t  full[FE_SLOTS], empty[FE_SLOTS];
 };
-constexpr int FE_CTL_BYTES = (sizeof(FeCtl) + 127) / 128 * 128;
-struct FeSmem {
-    FeCtl&   c;
-    uint8_t* stage_base;
-    FePiece* piece_base;
-    __device__ __forceinline__ uint8_t* stage(int slot) const { return stage_base + slot * FE_STAGE; }
-    __device__ __forceinline__ FePiece* piece(int slot) const { return piece_base + slot * FE_MAXP; }
-};
-static size_t fe_smem_bytes(int nslots) { return FE_CTL_BYTES + (size_t)nslots * (FE_STAGE + FE_MAXP * sizeof(FePiece)); }
+static_assert(4 * (sizeof(FeSmem) + 1024) <= 228 * 1024, "four CTAs per SM");
 
 // consumer threads (index ct of FE_CONSUMERS): n bytes from shared memory (any alignment) to global (any alignment)
 __device__ __forceinline__ void consumers_copy_from_smem(uint8_t* __restrict__ dst, const uint8_t* sp, int n, int ct)
@@ -414,13 +407,10 @@ __device__ __forceinline__ uint8_t fe_header_char(const FeHeader& H, int q)
 template <int MODE>
 __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, int64_t n_tiles)
 {
-    extern __shared__ __align__(128) uint8_t fe_raw[];
-    const int    nslots = a.n_slots;
-    const FeSmem sm{*reinterpret_cast<FeCtl*>(fe_raw), fe_raw + FE_CTL_BYTES,
-                    reinterpret_cast<FePiece*>(fe_raw + FE_CTL_BYTES + (size_t)nslots * FE_STAGE)};
-    FeCtl&       s = sm.c;
+    extern __shared__ __align__(16) uint8_t fe_raw[];
+    FeSmem& s = *reinterpret_cast<FeSmem*>(fe_raw);
     if (threadIdx.x == 0) {
-        for (int k = 0; k < nslots; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], FE_CONSUMERS / 32); }
+        for (int k = 0; k < FE_SLOTS; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], FE_CONSUMERS / 32); }
     }
     __syncthreads();
     const int64_t T0 = a.w0 / FASTA_TILE;
@@ -488,7 +478,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
                 const int      used = limit > 0 ? __shfl_sync(0xffffffffu, incl, limit - 1) : 0;
                 const bool     mine = emit && lane < limit;
                 if (mine) {
-                    FePiece& pc = sm.piece(slot)[idx];
+                    FePiece& pc = s.piece[slot][idx];
                     const int soff = incl - bytes + (int)(srcoff - al);
                     const int avail = bytes - (int)(srcoff - al);
                     pc.O = O; pc.src = a.seq + srcoff; pc.frag = (int)(gb + lane); pc.n = n;
@@ -510,8 +500,8 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
                     else mbar_arrive(&s.full[slot]);
                 }
                 __syncwarp();
-                if (mine && bytes > 0) tma_load_1d(sm.stage(slot) + (incl - bytes), a.seq + al, (uint32_t)bytes, &s.full[slot]);
-                if (++slot == nslots) { slot = 0; ph ^= 1; }
+                if (mine && bytes > 0) tma_load_1d(s.stage[slot] + (incl - bytes), a.seq + al, (uint32_t)bytes, &s.full[slot]);
+                if (++slot == FE_SLOTS) { slot = 0; ph ^= 1; }
             }
             if (done) break;
         }
@@ -528,7 +518,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
         if (np < 0) break;
         const int64_t x0 = s.x0[slot], x1 = s.x1[slot];
         for (int k = 0; k < np; k++) {
-            const FePiece& pc = sm.piece(slot)[k];
+            const FePiece& pc = s.piece[slot][k];
             const int64_t  O = pc.O;
             const int      h = pc.h;
             const int64_t  hp0 = O > x0 ? O : x0, hp1 = (O + h) < x1 ? (O + h) : x1;
@@ -559,33 +549,24 @@ __global__ void __launch_bounds__(FE_THREADS, 4) k_fasta_emit(FastaEmitArgs a, i
             if (ct == 0 && s1 >= x0 && s1 < x1) a.dst[s1 - a.w0] = '\n';
             if (pc.n > 0) {
                 uint8_t* d = a.dst + ((s0 > x0 ? s0 : x0) - a.w0);
-                consumers_copy_from_smem(d, sm.stage(slot) + pc.soff, pc.n_stage, ct);
+                consumers_copy_from_smem(d, s.stage[slot] + pc.soff, pc.n_stage, ct);
                 for (int q = pc.n_stage + ct; q < pc.n; q += FE_CONSUMERS) d[q] = pc.src[q]; // arena tail not covered by the bulk copy
             }
             if (hv) a.dst[hp0 + ct - a.w0] = hc;
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&s.empty[slot]); // this warp no longer reads the slot
-        if (++slot == nslots) { slot = 0; ph ^= 1; }
+        if (++slot == FE_SLOTS) { slot = 0; ph ^= 1; }
     }
 }
-void launch_fasta_emit(const FastaEmitArgs& a_in, cudaStream_t st)
+void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
 {
-    if (a_in.w1 <= a_in.w0 || a_in.G <= 0) return;
-    FastaEmitArgs a = a_in;
-    // Two CTAs of four pipeline slots per SM keep 96 KiB of bulk loads in flight per SM, and their shared memory
-    // (2 x 77 KiB) and registers (2 x 16 K) leave room for three CTAs of the coverage.txt emitter on the other emit
-    // lane: the gather is HBM-bound, the text emitter issue-bound, so the two overlap.
-    int per_sm = 2;
-    a.n_slots = 4;
-    if (const char* e = getenv("RAFT_B200_FE_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= FE_MAX_SLOTS) a.n_slots = v; } // tuning knobs
-    if (const char* e = getenv("RAFT_B200_FE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 4) per_sm = v; }
+    if (a.w1 <= a.w0 || a.G <= 0) return;
     int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
-    int64_t grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
-    const size_t smem = fe_smem_bytes(a.n_slots);
+    int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
     auto go = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<(unsigned)grid, FE_THREADS, smem, st>>>(a, tiles);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
+        kern<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);
     };
     if (a.split_len > 0) go(k_fasta_emit<2>);
     else if (a.sim) go(k_fasta_emit<1>);

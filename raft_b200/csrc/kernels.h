@@ -242,7 +242,6 @@ struct FastaEmitArgs {
     const int32_t* tile_frag; // record containing stream byte T*FASTA_TILE, for every tile of the stream
     int64_t        seq_safe_end; // bytes of the arena that may be read in 16-byte blocks (multiple of 16)
     const SimInfo* sim;          // null for real reads
-    int            n_slots;      // pipeline slots per CTA (set by the launcher)
     int            split_len;    // > 0: split_naive records  ">" name "_" k "\n" bases "\n"  with k = a / split_len + 1
 };
 void launch_fasta_tile_index(const int64_t* frag_off, int64_t G, int32_t* tile_frag, cudaStream_t st);
