@@ -11,7 +11,7 @@ LIB       := raft_b200/libraft_b200.so
 
 all: $(LIB) raft_b200/raft raft_b200/split_naive raft_b200/libraft_synth.so oracle
 
-$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh $(SRC)/coverage.cuh $(SRC)/covtext.cuh include/raft_b200.h
+$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh $(SRC)/coverage.cuh include/raft_b200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -1110,10 +1110,6 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
         ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
         ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0; ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
-        // measured: throttling the text emitter to leave SM slots for the gather (2 CTAs/SM) doubles its time and the two
-        // kernels still do not co-reside (the gather's 4 x 256 x 64 registers fill the register file); a persistent grid
-        // of 6 CTAs/SM is also ~20 % slower than one CTA per tile (hardware CTA scheduling balances the tiles better)
-        ca.ctas_per_sm = 0;
         launch_cov_emit(ca, t1 - t0, st);
         CKL();
     } else if (which == RAFTGPU_OUT_LONG_REPEATS) {

@@ -11,7 +11,6 @@
 // the target side too when overlaps are not symmetric and target != query.
 // Bin range of [s, e) (repeat.hpp:62-77): lo = max(s,0)/reso, bins lo..(e-1)/reso when e-1 >= lo*reso.
 #include "coverage.cuh"
-#include "covtext.cuh"
 
 namespace raftk {
 

@@ -7,126 +7,196 @@
 //                                                                                (chop.hpp:261-265,314-318)
 //
 // K5a is slot-parallel (a slot is one bin, or the per-read sentinel that carries the newline):
-// a tile of 1024 slots is formatted into shared memory at the same 16-byte phase as its
-// destination and then stored with aligned 128-bit writes.  K5b is output-tile-parallel: every CTA
+// one warp per tile of 1024 slots formats 32 slots at a time into shared memory at the same 16-byte
+// phase as its destination and stores them with aligned 128-bit writes.  K5b is output-tile-parallel: every CTA
 // owns 16 KiB of the output file, finds the fragments that intersect it by binary search over the
 // record offsets, generates header bytes on the fly and gathers sequence bytes with aligned
 // 128-bit loads + funnel shifts + aligned 128-bit stores (stream-compacted: bytes land in their
 // final file order).
 #include <cstdlib>
 
-#include "covtext.cuh"
+#include "kernels.h"
 
 namespace raftk {
 
 // ================================================================ K5a coverage.txt
-constexpr int CE_THREADS = 256;
-constexpr int CE_PER = COV_TILE_SLOTS / CE_THREADS; // 4 slots per thread
-constexpr int CE_MAX_SLOT_BYTES = 40;               // "read 2147483647 " (16) + "2147483647,-2147483648 " (23)
-constexpr int CE_CAP = 16384;                       // shared-memory text buffer; tiles with more text (tiny reads) use the direct path
-constexpr int CE_SMEM = CE_CAP + 32;
+// One warp per 1024-slot tile (a slot is one bin, or the per-read sentinel that carries the newline); the tile's
+// stream offset comes from the scan of the per-tile text sizes.  The warp walks its tile in 8 chunks of 128 slots,
+// four consecutive slots per lane: one 128-bit coverage load per lane (the next chunk's load is already in
+// flight), per-lane text size, warp scan, SWAR decimal conversion (four digits per multiply chain) into a per-warp
+// shared buffer laid out at the 16-byte phase of its destination, then aligned 128-bit stores.  No block-level
+// barrier and no per-thread search: the read a slot belongs to is warp-uniform state that only moves when a chunk
+// reaches the end of the current read.
+constexpr int CW_WARPS = 8;
+constexpr int CW_THREADS = CW_WARPS * 32;
+constexpr int CW_PER = 4;             // slots per lane per chunk
+constexpr int CW_CHUNK = 32 * CW_PER;
+constexpr int CW_BUF = 2048;          // per-warp text buffer
+constexpr int CW_CAP = CW_BUF - 16;   // chunks with more text (tiny reads: many "read i " prefixes) take the direct path
+constexpr int CW_MAX_SLOT_BYTES = 40; // "read 2147483647 " (16) + "2147483647,-2147483648 " (23)
 
-// text of this thread's slots at p (shared or local memory after inlining); returns the end
-__device__ __forceinline__ uint8_t* cov_format_slots(uint8_t* p, SlotWalk w, int nmine, const int* cv, const int* dg, int reso, int64_t own_first)
+// ASCII of the four decimal digits of n < 10000, most significant digit in the low byte
+__device__ __forceinline__ unsigned ascii4(unsigned n)
 {
-#pragma unroll
-    for (int k = 0; k < CE_PER; k++) {
-        if (k < nmine) {
-            if (w.bin == 0) {
-                p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
-                uint64_t id = (uint64_t)(own_first + w.r);
-                int      nd = dec_digits64(id);
-                for (int d = nd - 1; d >= 0; d--) { p[d] = (uint8_t)('0' + (unsigned)(id % 10ull)); id /= 10ull; }
-                p += nd; *p++ = ' ';
-            }
-            if (w.left == 1) {
-                *p++ = '\n';
-            } else {
-                p = put_u32_nd(p, (uint32_t)w.bin * (uint32_t)reso, dg[k] & 15); *p++ = ',';
-                if (dg[k] >> 8) *p++ = '-';
-                p = put_u32_nd(p, cv[k] < 0 ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], (dg[k] >> 4) & 15); *p++ = ' ';
-            }
-            w.next();
-        }
+    const unsigned q = (n * 5243u) >> 19;                 // n / 100
+    const unsigned x = q + ((n - q * 100u) << 16);        // two two-digit lanes
+    const unsigned t = ((x * 103u) >> 10) & 0x000F000Fu;  // tens of each lane
+    return (t + ((x - t * 10u) << 8)) | 0x30303030u;
+}
+// the nd decimal digits of v at p; every branch is on nd, which is nearly warp-uniform for bin positions
+__device__ __forceinline__ void put_dec(uint8_t* p, unsigned v, int nd)
+{
+    if (nd <= 2) { // v < 100
+        const unsigned t = (v * 103u) >> 10, o = v - t * 10u;
+        if (nd == 2) { p[0] = (uint8_t)('0' + t); p[1] = (uint8_t)('0' + o); }
+        else p[0] = (uint8_t)('0' + o);
+    } else if (nd <= 4) {
+        const unsigned A = ascii4(v) >> (nd == 3 ? 8 : 0);
+        p[0] = (uint8_t)A; p[1] = (uint8_t)(A >> 8); p[2] = (uint8_t)(A >> 16);
+        if (nd == 4) p[3] = (uint8_t)(A >> 24);
+    } else if (nd <= 8) {
+        const unsigned hi = v / 10000u, A = ascii4(hi), B = ascii4(v - hi * 10000u);
+        const unsigned sh = 8u * (8u - (unsigned)nd);     // 0, 8, 16, 24: drop the leading zeros of the 8-digit field
+        const unsigned lo = __funnelshift_r(A, B, sh), up = B >> sh;
+        p[0] = (uint8_t)lo; p[1] = (uint8_t)(lo >> 8); p[2] = (uint8_t)(lo >> 16); p[3] = (uint8_t)(lo >> 24);
+        p[4] = (uint8_t)up;
+        if (nd > 5) p[5] = (uint8_t)(up >> 8);
+        if (nd > 6) p[6] = (uint8_t)(up >> 16);
+        if (nd > 7) p[7] = (uint8_t)(up >> 24);
+    } else {
+        put_u32_nd(p, v, nd);
     }
-    return p;
+}
+// text of one slot at p (shared or local memory after inlining)
+__device__ __forceinline__ uint8_t* cov_slot_format(uint8_t* p, bool first, bool sentinel, bool neg, unsigned pos, int dpos, unsigned ucov, int dcov,
+                                                    unsigned read_id)
+{
+    if (first) {
+        p[0] = 'r'; p[1] = 'e'; p[2] = 'a'; p[3] = 'd'; p[4] = ' '; p += 5;
+        const int nd = dec_digits(read_id); // read ids are ints in the reference (repeat.hpp:105)
+        put_dec(p, read_id, nd);
+        p += nd; *p++ = ' ';
+    }
+    if (sentinel) { *p++ = '\n'; return p; }
+    put_dec(p, pos, dpos); p[dpos] = ','; p += dpos + 1;
+    if (neg) *p++ = '-';
+    put_dec(p, ucov, dcov); p[dcov] = ' ';
+    return p + dcov + 1;
+}
+// rare (dozens of tiny reads in one chunk): format privately, store byte-wise with clipping
+__device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int whi, bool first, bool sentinel, bool neg, unsigned pos, int dpos,
+                                            unsigned ucov, int dcov, unsigned read_id)
+{
+    uint8_t  loc[CW_MAX_SLOT_BYTES];
+    uint8_t* e = cov_slot_format(loc, first, sentinel, neg, pos, dpos, ucov, dcov, read_id);
+    for (uint8_t* q = loc; q < e; q++, x++) if (x >= wlo && x < whi) gbase[x] = *q;
+    return x;
 }
 
-template <bool EMIT>
-__device__ __forceinline__ void cov_text_tile(const CovEmitArgs& a, const int64_t tile, uint8_t* sbuf, int* ws)
+__global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64_t n_tiles)
 {
-    const int64_t  g0 = tile * COV_TILE_SLOTS + (int64_t)threadIdx.x * CE_PER;
-    const int      nmine = g0 >= a.n_slots ? 0 : (a.n_slots - g0 < CE_PER ? (int)(a.n_slots - g0) : CE_PER);
-    int            mine = 0;
-    int            cv[CE_PER], dg[CE_PER];
-    SlotWalk       w0;
-    if (nmine) {
-        // the tile map bounds the search to the reads that intersect this tile
+    __shared__ __align__(16) uint8_t sbuf[CW_WARPS][CW_BUF];
+    const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tl = (int64_t)blockIdx.x * CW_WARPS + warp;
+    if (tl >= n_tiles) return;
+    const int64_t tile = a.tile_first + tl;
+    const int64_t oc0 = a.tile_off[tile];
+    if (a.tile_off[tile + 1] <= a.w0 || oc0 >= a.w1) return;
+    const int64_t g0 = tile * COV_TILE_SLOTS;
+    // read holding the tile's first slot: the tile map bounds the search to the reads that intersect the tile
+    int64_t r;
+    {
         int64_t lo = a.tile_read[tile], hi = (int64_t)a.tile_read[tile + 1] + 1;
         while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (a.slot_off[mid] <= g0) lo = mid; else hi = mid; }
-        w0.init(a.slot_off, lo, g0);
+        r = lo;
     }
-    if (nmine == CE_PER) { // 4 consecutive ints, 16-byte aligned
-        int4 v = *reinterpret_cast<const int4*>(a.cov + g0);
-        cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w;
-    } else {
+    // everything inside the tile is 32-bit and relative: slots to g0, text bytes to oc0
+    constexpr int FAR = 1 << 20;
+    auto rel = [&](int64_t slot) { const int64_t d = slot - g0; return d > FAR ? FAR : (int)d; }; // a read has < 2^31 slots
+    int            rs = rel(a.slot_off[r]), re = rel(a.slot_off[r + 1]), mr = 0; // warp-uniform: read of the chunk's first slot (= r + mr)
+    const int      nvalid = a.n_slots - g0 < COV_TILE_SLOTS ? (int)(a.n_slots - g0) : COV_TILE_SLOTS;
+    const int64_t  dlo = a.w0 - oc0, dhi = a.w1 - oc0;
+    const int      wlo = dlo < 0 ? 0 : (dlo > (1 << 30) ? (1 << 30) : (int)dlo), whi = dhi > (1 << 30) ? (1 << 30) : (int)dhi;
+    uint8_t* const gbase = a.dst + (oc0 - a.w0); // byte 0 of the tile's text (only dereferenced inside the window)
+    const int      gl = (int)((uintptr_t)gbase & 15);
+    const int32_t* covp = a.cov + g0;
+    uint8_t*       wb = sbuf[warp];
+    const unsigned reso = (unsigned)a.reso, rid0 = (unsigned)(a.own_first + r); // global id of read r
+    auto load4 = [&](int s) { // coverage of slots s .. s+3 of the tile
+        if (s + 3 < nvalid) return *reinterpret_cast<const int4*>(covp + s);
+        int4 v;
+        v.x = s < nvalid ? covp[s] : 0; v.y = s + 1 < nvalid ? covp[s + 1] : 0; v.z = s + 2 < nvalid ? covp[s + 2] : 0; v.w = 0;
+        return v;
+    };
+    int  ro = 0; // text offset of the chunk inside the tile
+    int4 cvn = load4(CW_PER * lane);
+    for (int sl0 = 0; sl0 < nvalid; sl0 += CW_CHUNK) {
+        const int  s0 = sl0 + CW_PER * lane;
+        const int4 cq = cvn;
+        if (sl0 + CW_CHUNK < nvalid) cvn = load4(s0 + CW_CHUNK);
+        const int cv[CW_PER] = {cq.x, cq.y, cq.z, cq.w};
+        // read of this lane's first slot
+        int        lrs = rs, lre = re, lmr = mr;
+        const bool crossing = sl0 + CW_CHUNK - 1 >= re - 1; // the chunk reaches this read's sentinel
+        if (crossing) while (s0 < nvalid && s0 >= lre) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
+        const int frs = lrs, fre = lre, fmr = lmr; // the format pass restarts here
+        // pass 1: sizes
+        int size = 0, meta[CW_PER];
 #pragma unroll
-        for (int k = 0; k < CE_PER; k++) cv[k] = (k < nmine) ? a.cov[g0 + k] : 0;
-    }
-    {
-        SlotWalk w = w0;
-#pragma unroll
-        for (int k = 0; k < CE_PER; k++) {
-            dg[k] = 0;
-            if (k < nmine) {
-                if (w.bin == 0) mine += 5 + dec_digits64((uint64_t)(a.own_first + w.r)) + 1;
-                if (w.left == 1) mine += 1;
-                else { dg[k] = slot_digits(w.bin, a.reso, cv[k]); mine += (dg[k] & 15) + ((dg[k] >> 4) & 15) + (dg[k] >> 8) + 2; }
-                w.next();
+        for (int k = 0; k < CW_PER; k++) {
+            const int      s = s0 + k;
+            const bool     sentinel = s == lre - 1, neg = cv[k] < 0;
+            const unsigned ucov = neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k];
+            const int      dpos = dec_digits((unsigned)(s - lrs) * reso), dcov = ucov < 100u ? 1 + (int)(ucov > 9u) : dec_digits(ucov);
+            meta[k] = dpos | (dcov << 4);
+            if (s < nvalid) {
+                size += sentinel ? 1 : dpos + dcov + 2 + (int)neg;
+                if (s == lrs) size += 6 + dec_digits(rid0 + (unsigned)lmr);
+                if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); } // the next slot starts the next read
             }
         }
-    }
-    int tot;
-    int ex = block_exclusive_sum<int, CE_THREADS>(mine, ws, &tot);
-    if (!EMIT) {
-        if (threadIdx.x == 0) a.tile_bytes[tile] = tot;
-        return;
-    }
-    const int64_t o0 = a.tile_off[tile], o1 = o0 + tot;
-    const int64_t c0 = o0 > a.w0 ? o0 : a.w0, c1 = o1 < a.w1 ? o1 : a.w1;
-    if (c0 >= c1) return;
-    const uintptr_t gdst0 = (uintptr_t)a.dst + (uintptr_t)(o0 - a.w0); // address of stream byte o0 (may precede dst)
-    const int       phase = (int)(gdst0 & 15);
-    if (tot > a.text_cap) { // rare (thousands of tiny reads in one tile): format privately, store byte-wise with clipping
-        uint8_t  loc[CE_PER * CE_MAX_SLOT_BYTES];
-        uint8_t* e = cov_format_slots(loc, w0, nmine, cv, dg, a.reso, a.own_first);
-        int64_t  x = o0 + ex;
-        for (uint8_t* q = loc; q < e; q++, x++) if (x >= a.w0 && x < a.w1) a.dst[x - a.w0] = *q;
-        return;
-    }
-    cov_format_slots(sbuf + phase + ex, w0, nmine, cv, dg, a.reso, a.own_first);
-    __syncthreads();
-    // store [c0, c1): head bytes, aligned 128-bit body, tail bytes
-    const uintptr_t ga0 = gdst0 + (uintptr_t)(c0 - o0), ga1 = gdst0 + (uintptr_t)(c1 - o0);
-    uintptr_t       fa = (ga0 + 15) & ~(uintptr_t)15, la = ga1 & ~(uintptr_t)15;
-    if (fa > la) { fa = ga1; la = ga1; }
-    const uint8_t* sb = sbuf + phase; // sb[x - gdst0] is the byte for address x
-    for (uintptr_t x = ga0 + threadIdx.x; x < fa; x += CE_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
-    for (uintptr_t x = fa + (uintptr_t)threadIdx.x * 16; x < la; x += (uintptr_t)CE_THREADS * 16)
-        stg_stream(reinterpret_cast<uint4*>(x), *reinterpret_cast<const uint4*>(sb + (x - gdst0)));
-    for (uintptr_t x = la + threadIdx.x; x < ga1; x += CE_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
-}
-
-// Persistent over tiles [tile_first, tile_first + n_tiles): the grid is sized by the launcher (all SM slots when the
-// emitter runs alone, two CTAs per SM when it shares the GPU with the gather kernel on the other emit stream).
-template <bool EMIT>
-__global__ void __launch_bounds__(CE_THREADS, EMIT ? 6 : 8) k_cov_text(CovEmitArgs a, int64_t n_tiles)
-{
-    extern __shared__ __align__(16) uint8_t sbuf[];
-    __shared__ int ws[34];
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        cov_text_tile<EMIT>(a, a.tile_first + t, sbuf, ws);
-        __syncthreads(); // the shared text buffer and the scan scratch are reused by the next tile
+        const int incl = warp_inclusive_sum(size), ex = incl - size;
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (crossing) { mr = __shfl_sync(0xffffffffu, lmr, 31); rs = __shfl_sync(0xffffffffu, lrs, 31); re = __shfl_sync(0xffffffffu, lre, 31); }
+        const int c0 = ro > wlo ? ro : wlo, c1 = ro + tot < whi ? ro + tot : whi;
+        if (c0 < c1) {
+            lrs = frs; lre = fre; lmr = fmr;
+            if (tot <= a.text_cap) {
+                const int phase = (gl + ro) & 15;
+                uint8_t*  p = wb + phase + ex;
+#pragma unroll
+                for (int k = 0; k < CW_PER; k++) {
+                    const int s = s0 + k;
+                    if (s < nvalid) {
+                        const bool sentinel = s == lre - 1, neg = cv[k] < 0;
+                        p = cov_slot_format(p, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso, meta[k] & 15,
+                                            neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], meta[k] >> 4, rid0 + (unsigned)lmr);
+                        if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
+                    }
+                }
+                __syncwarp();
+                int fa = c0 + ((16 - ((gl + c0) & 15)) & 15), la = c1 - ((gl + c1) & 15); // 16-byte aligned part of [c0, c1)
+                if (fa > la) { fa = c1; la = c1; }
+                const uint8_t* sb = wb + (phase - ro); // sb[x] is byte x of the tile's text
+                if (c0 + lane < fa) gbase[c0 + lane] = sb[c0 + lane];
+#pragma unroll 1
+                for (int x = fa + lane * 16; x < la; x += 512) stg_stream(reinterpret_cast<uint4*>(gbase + x), *reinterpret_cast<const uint4*>(sb + x));
+                if (la + lane < c1) gbase[la + lane] = sb[la + lane];
+                __syncwarp(); // the buffer is rewritten by the next chunk
+            } else {
+                int x = ro + ex;
+                for (int k = 0; k < CW_PER; k++) {
+                    const int s = s0 + k;
+                    if (s < nvalid) {
+                        const bool sentinel = s == lre - 1, neg = cv[k] < 0;
+                        x = cov_slot_direct(gbase, x, wlo, whi, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso, meta[k] & 15,
+                                            neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], meta[k] >> 4, rid0 + (unsigned)lmr);
+                        if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
+                    }
+                }
+            }
+        }
+        ro += tot;
     }
 }
 
@@ -146,21 +216,13 @@ void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, 
 }
 
 int  cov_tiles(int64_t n_slots) { return (int)((n_slots + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS); }
-void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st)
-{
-    int t = cov_tiles(a.n_slots);
-    if (t > 0) k_cov_text<false><<<t, CE_THREADS, 0, st>>>(a, (int64_t)t);
-}
 void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream_t st)
 {
     if (n_tiles_launch <= 0) return;
     CovEmitArgs a = a_in;
-    a.text_cap = CE_CAP;
-    if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CE_CAP) a.text_cap = v; } // test knob: force the direct path
-    cudaFuncSetAttribute(k_cov_text<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CE_SMEM);
-    // ctas_per_sm == 0: one CTA per tile (the loop in the kernel runs once)
-    const int64_t grid = a.ctas_per_sm > 0 && n_tiles_launch > 148 * (int64_t)a.ctas_per_sm ? 148 * (int64_t)a.ctas_per_sm : n_tiles_launch;
-    k_cov_text<true><<<(unsigned)grid, CE_THREADS, CE_SMEM, st>>>(a, n_tiles_launch);
+    a.text_cap = CW_CAP;
+    if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CW_CAP) a.text_cap = v; } // test knob: force the direct path
+    k_cov_text<<<(unsigned)((n_tiles_launch + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, st>>>(a, n_tiles_launch);
 }
 
 // ================================================================ K5c long_repeats.txt

@@ -181,19 +181,16 @@ struct CovEmitArgs {
     int64_t        m, n_slots;
     int64_t        own_first; // global id of local read 0
     int            reso;
-    const int64_t* tile_off;  // n_tiles+1 (bytes), null for the sizing pass
-    int32_t*       tile_bytes; // sizing pass output
+    const int64_t* tile_off;  // n_tiles+1 (bytes)
     uint8_t*       dst;       // window buffer: byte (w0 + k) of the stream goes to dst[k]
     int64_t        w0, w1;
     int64_t        tile_first; // first tile of this launch
     const int32_t* tile_read;  // n_tiles+1: read containing the tile's first slot (last entry = m-1 sentinel)
-    int            text_cap;   // tiles with more text than this take the direct (byte-wise) path
-    int            ctas_per_sm; // > 0: persistent grid of 148 x this; 0: one CTA per tile
+    int            text_cap;   // 32-slot chunks with more text than this take the direct (byte-wise) path
 };
 // tile_read[T] = read whose slots contain slot T*COV_TILE_SLOTS
 void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, int32_t* tile_read, cudaStream_t st);
 int  cov_tiles(int64_t n_slots);
-void launch_cov_sizes(const CovEmitArgs& a, cudaStream_t st);
 void launch_cov_emit(const CovEmitArgs& a, int64_t n_tiles_launch, cudaStream_t st);
 
 // long_repeats.bed (simulated reads only, repeat.hpp:187-199): chr \t x \t y \n per repeat
