@@ -297,20 +297,24 @@ def ours(a):
                 seq_keep = None
                 torch.cuda.empty_cache()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for r0 in range(0, ds.n, chunk_reads):
-                r1 = min(ds.n, r0 + chunk_reads)
-                tbuf, nb = synth_gpu.gen_fasta_text(ds, r0, r1, tbuf)
-                torch.cuda.synchronize()
-                f0.record()
-                ctxf.ingest_fasta(tbuf, nb, last=(r1 == ds.n), total_hint=total_text)
-                f1.record()
-                torch.cuda.synchronize()
-                ms_f += f0.elapsed_time(f1)
+            for timed in (False, True):  # first pass untimed: it pays the one-time cudaMalloc of the ~100 GB arena
+                if timed:
+                    ctxf.reset()
+                ms_f = 0.0
+                for r0 in range(0, ds.n, chunk_reads):
+                    r1 = min(ds.n, r0 + chunk_reads)
+                    tbuf, nb = synth_gpu.gen_fasta_text(ds, r0, r1, tbuf)
+                    torch.cuda.synchronize()
+                    f0.record()
+                    ctxf.ingest_fasta(tbuf, nb, last=(r1 == ds.n), total_hint=total_text)
+                    f1.record()
+                    torch.cuda.synchronize()
+                    ms_f += f0.elapsed_time(f1)
             ok = ctxf.stats().n_reads == 0  # stats are filled by run(); check the read count through a table instead
             nb_off = ctxf.table(api.TAB_BIN_OFF)
             fasta_ingest = {"text_bytes": total_text, "ms": ms_f, "gbs_text": total_text / (ms_f / 1e3) / 1e9,
                             "alg_gbs": (total_text + ds.bases) / (ms_f / 1e3) / 1e9, "reads": int(len(nb_off) - 1),
-                            "note": "raftgpu_ingest_fasta on device-resident text, ~2 GiB chunks; includes layout scans + name table of the last call"}
+                            "note": "raftgpu_ingest_fasta on device-resident text, ~2 GiB chunks, second pass over a reset context (arena already allocated); includes layout scans + name table of the last call"}
             ctxf.close()
             del tbuf
             if seq_keep is None:
@@ -421,6 +425,12 @@ def ours(a):
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner, child processes) are
+    # sent to stderr, and sys.stdout is re-pointed at the saved descriptor for our own print of the result
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

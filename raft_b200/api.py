@@ -175,6 +175,11 @@ class Context:
         """Queue the emitter for a device destination; pair with sync()."""
         self._ck(self.L.raftgpu_fetch_async(self._h, which, off, _ptr(dst), n))
 
+    def reset(self):
+        """Forget reads, PAF and results; device buffers stay allocated for the next run."""
+        self._ck(self.L.raftgpu_reset(self._h))
+        self._keep = []
+
     def sync(self):
         self._ck(self.L.raftgpu_sync(self._h))
 
