@@ -100,7 +100,7 @@ struct raftgpu_ctx {
     Misc*   misc() const { return b_misc.as<Misc>(); }
 
     // coverage + K3 + layout
-    DevBuf  b_cov; bool diff_zeroed = false, finalized = false, sized = false;
+    DevBuf  b_cov, b_diff; bool diff_zeroed = false, finalized = false, sized = false;
     DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
     DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_static, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
@@ -654,7 +654,7 @@ static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
         a.status = ctx->b_status.as<uint64_t>(); a.ticket = &M->ticket; a.sym_flag = &M->sym_flag; a.err = &M->err;
         a.n_records_out = (int64_t*)&M->n_records_out; a.names = ctx->nt;
         // a retry (record capacity overflow) decodes the same lines again: their query sides are already in
-        a.diff = attempt == 0 ? ctx->b_cov.as<int32_t>() : nullptr; a.slot_off = ctx->b_slot_off.as<int64_t>(); a.reso = ctx->prm.reso;
+        a.diff = attempt == 0 ? ctx->b_diff.as<int32_t>() : nullptr; a.slot_off = ctx->b_slot_off.as<int64_t>(); a.reso = ctx->prm.reso;
         a.own_first = ctx->own_first; a.own_count = ctx->m; a.err_range = &M->err_range;
         CK(launch_paf_tokenize(a, ctx->st));
         ctx->launches++;
@@ -781,7 +781,7 @@ static ScatterArgs scatter_args(raftgpu_ctx* ctx)
     ScatterArgs a{};
     a.qid = ctx->b_qid.as<int32_t>(); a.tid = ctx->b_tid.as<int32_t>(); a.qs = ctx->b_qs.as<int32_t>(); a.qe = ctx->b_qe.as<int32_t>();
     a.ts = ctx->b_ts.as<int32_t>(); a.te = ctx->b_te.as<int32_t>(); a.n_rec = ctx->n_rec;
-    a.slot_off = ctx->b_slot_off.as<int64_t>(); a.diff = ctx->b_cov.as<int32_t>(); a.reso = ctx->prm.reso;
+    a.slot_off = ctx->b_slot_off.as<int64_t>(); a.diff = ctx->b_diff.as<int32_t>(); a.reso = ctx->prm.reso;
     a.own_first = ctx->own_first; a.own_count = ctx->m; a.sym_flag = &ctx->misc()->sym_flag; a.err = &ctx->misc()->err;
     return a;
 }
@@ -789,8 +789,8 @@ static ScatterArgs scatter_args(raftgpu_ctx* ctx)
 static int zero_diff(raftgpu_ctx* ctx)
 {
     if (ctx->diff_zeroed) return RAFTGPU_OK;
-    CK(ctx->b_cov.ensure(sizeof(int32_t) * (size_t)(ctx->n_slots + 8)));
-    CK(cudaMemsetAsync(ctx->b_cov.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st));
+    CK(ctx->b_diff.ensure(sizeof(int32_t) * (size_t)(ctx->n_slots + 8)));
+    CK(cudaMemsetAsync(ctx->b_diff.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st));
     ctx->diff_zeroed = true;
     return RAFTGPU_OK;
 }
@@ -830,7 +830,7 @@ extern "C" int raftgpu_accumulate_endpoints(raftgpu_ctx* ctx, const void* ep, in
     CK(cudaSetDevice(ctx->device));
     int st = zero_diff(ctx);
     if (st) return st;
-    launch_scatter_endpoints((const int32_t*)ep, count, ctx->b_slot_off.as<int64_t>(), ctx->b_cov.as<int32_t>(), ctx->prm.reso, ctx->own_first,
+    launch_scatter_endpoints((const int32_t*)ep, count, ctx->b_slot_off.as<int64_t>(), ctx->b_diff.as<int32_t>(), ctx->prm.reso, ctx->own_first,
                              ctx->m, &ctx->misc()->err, ctx->st);
     CKL();
     CK(cudaStreamSynchronize(ctx->st));
@@ -886,8 +886,9 @@ extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
     // K2b: coverage = inclusive scan of the difference array
     cudaEventRecord(ctx->ev[3], ctx->st);
     CK(ctx->b_status.ensure(sizeof(uint64_t) * (size_t)(scan_tiles_cov(ctx->n_slots) + scan_tiles_small(std::max<int64_t>(m, ctx->cut_cap_total + m)) + 16)));
-    CovSizeArgs cs{ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_static.as<int32_t>()};
-    launch_scan_cov_inplace(ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, cs, ctx->st);
+    CovSizeArgs cs{ctx->b_cov_tile_bytes.as<int32_t>(), ctx->b_cov_tile_static.as<int32_t>(), ctx->b_slot_off.as<int64_t>(), ctx->b_cov_tile_read.as<int32_t>()};
+    CK(ctx->b_cov.ensure(sizeof(int32_t) * (size_t)(ctx->n_slots + 8)));
+    launch_scan_cov(ctx->b_diff.as<int32_t>(), ctx->b_cov.as<int32_t>(), ctx->n_slots, ctx->b_status.as<uint64_t>(), &M->ticket, cs, ctx->st);
     CKL();
     cudaEventRecord(ctx->ev[4], ctx->st);
     // K3: repeats + cut points

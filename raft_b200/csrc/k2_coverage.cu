@@ -130,15 +130,32 @@ __device__ __forceinline__ int cov_dyn_bytes(int c)
     const unsigned u = c < 0 ? (unsigned)(-(int64_t)c) : (unsigned)c;
     return (u < 100u ? (u < 10u ? 3 : 4) : dec_digits(u) + 2) + (c < 0);
 }
-__global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ data, int64_t n, uint64_t* status, int* ticket, CovSizeArgs cs)
+// The slots of every read sum to zero (each +1 has its -1 at or before the read's sentinel), so the running sum
+// entering a tile is just the sum of the differences from the start of the read that spans the tile boundary
+// (tile_read gives that read) up to the tile: on average half a read (~1 KiB) re-read per 16 KiB tile, and no
+// communication between tiles.  Only when that read starts more than CS_BACK slots before the tile (reads longer
+// than ~200 kbp at -r 50) does the tile wait for its predecessor's running sum, which every tile publishes as soon
+// as it knows it; tile ids come from an atomic ticket so a waited-for tile is always resident or finished.  The
+// scan is out of place (diff -> cov) because the backward re-read must see differences, not coverages.
+constexpr int CS_BACK = CS_TILE; // longest backward re-read
+
+__global__ void __launch_bounds__(CS_THREADS) k_scan_cov(const int32_t* __restrict__ diff, int32_t* __restrict__ cov, int64_t n, uint64_t* status,
+                                                         int* ticket, CovSizeArgs cs)
 {
-    __shared__ int      ws[34];
-    __shared__ uint64_t bcast;
-    __shared__ int      s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+    __shared__ int     ws[34], wp[34];
+    __shared__ int     s_tile;
+    __shared__ int64_t s_rs;
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        s_tile = t;
+        s_rs = cs.slot_off[cs.tile_read[(int64_t)t * (CS_TILE / COV_TILE_SLOTS)]]; // first slot of the read holding the tile's first slot
+    }
+    const int lane = lane_id(), warp = warp_id();
     __syncthreads();
-    const int     tile = s_tile, lane = lane_id(), warp = warp_id();
-    const int64_t tbase = (int64_t)tile * CS_TILE + (int64_t)warp * (128 * CS_ROUNDS);
+    const int     tile = s_tile;
+    const int64_t t0 = (int64_t)tile * CS_TILE, tbase = t0 + (int64_t)warp * (128 * CS_ROUNDS);
+    const int64_t rs = s_rs;
+    const bool    local = t0 - rs <= CS_BACK; // uniform
     int4          v[CS_ROUNDS];
     int           rsum[CS_ROUNDS];
     const bool    full = (int64_t)(tile + 1) * CS_TILE <= n;
@@ -146,13 +163,16 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
     for (int r = 0; r < CS_ROUNDS; r++) {
         int64_t i = tbase + r * 128 + lane * 4;
         if (full) {
-            v[r] = *reinterpret_cast<const int4*>(data + i);
+            v[r] = *reinterpret_cast<const int4*>(diff + i);
         } else {
-            v[r].x = i + 0 < n ? data[i + 0] : 0; v[r].y = i + 1 < n ? data[i + 1] : 0;
-            v[r].z = i + 2 < n ? data[i + 2] : 0; v[r].w = i + 3 < n ? data[i + 3] : 0;
+            v[r].x = i + 0 < n ? diff[i + 0] : 0; v[r].y = i + 1 < n ? diff[i + 1] : 0;
+            v[r].z = i + 2 < n ? diff[i + 2] : 0; v[r].w = i + 3 < n ? diff[i + 3] : 0;
         }
         rsum[r] = v[r].x + v[r].y + v[r].z + v[r].w;
     }
+    int part = 0; // this thread's share of the differences between the spanning read's start and the tile
+    if (local)
+        for (int64_t i = rs + threadIdx.x; i < t0; i += CS_THREADS) part += diff[i];
     // lane-exclusive prefix inside each round, rounds chained
     int lane_ex[CS_ROUNDS], wtot = 0;
 #pragma unroll
@@ -161,13 +181,30 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
         lane_ex[r] = wtot + inc - rsum[r];
         wtot += __shfl_sync(FULL, inc, 31);
     }
-    // block: exclusive prefix over warp totals (one value per warp, carried by lane 31's slot)
-    int btot;
-    int bex = block_exclusive_sum<int, CS_THREADS>(lane == 31 ? wtot : 0, ws, &btot);
-    int warp_ex = __shfl_sync(FULL, bex, 31) - 0; // lane 31's exclusive prefix == sum of earlier warps
-    uint64_t pre = lookback_block(status, tile, (uint64_t)(int64_t)btot, &bcast);
-    int      p0 = (int)lb_signed(pre) + warp_ex;
-    int      text_bytes = 0;
+    // block: exclusive prefix over the warp totals, and the sum of the carry parts, in one pass
+    part = warp_sum(part);
+    if (lane == 0) { ws[warp] = wtot; wp[warp] = part; }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int NW = CS_THREADS / 32;
+        int w = lane < NW ? ws[lane] : 0, q = lane < NW ? wp[lane] : 0;
+        int wi = warp_inclusive_sum(w);
+        q = warp_sum(q);
+        if (lane < NW) ws[lane] = wi - w;
+        if (lane == NW - 1) {
+            int carry = q;
+            if (!local) { // the spanning read started long before: take the predecessor's running sum
+                uint64_t x;
+                while (((x = ld_relaxed_u64(status + tile - 1)) >> 62) == 0) __nanosleep(40);
+                carry = (int)lb_signed(x & LB_MASK);
+            }
+            st_relaxed_u64(status + tile, LB_PREFIX | ((uint64_t)(int64_t)(carry + wi) & LB_MASK)); // running sum after this tile
+            wp[32] = carry;
+        }
+    }
+    __syncthreads();
+    int p0 = wp[32] + ws[warp];
+    int text_bytes = 0;
 #pragma unroll
     for (int r = 0; r < CS_ROUNDS; r++) {
         int64_t i = tbase + r * 128 + lane * 4;
@@ -180,10 +217,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
                                (i + 2 < n ? cov_dyn_bytes(o.z) : 0) + (i + 3 < n ? cov_dyn_bytes(o.w) : 0);
         }
         if (full) {
-            *reinterpret_cast<int4*>(data + i) = o;
+            *reinterpret_cast<int4*>(cov + i) = o;
         } else {
-            if (i + 0 < n) data[i + 0] = o.x; if (i + 1 < n) data[i + 1] = o.y;
-            if (i + 2 < n) data[i + 2] = o.z; if (i + 3 < n) data[i + 3] = o.w;
+            if (i + 0 < n) cov[i + 0] = o.x; if (i + 1 < n) cov[i + 1] = o.y;
+            if (i + 2 < n) cov[i + 2] = o.z; if (i + 3 < n) cov[i + 3] = o.w;
         }
     }
     if (cs.tile_bytes) { // a warp's 512 slots lie inside one 1024-slot text tile
@@ -192,7 +229,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_cov(int32_t* __restrict__ d
     }
 }
 int  scan_tiles_cov(int64_t n) { return (int)((n + CS_TILE - 1) / CS_TILE); }
-void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st)
+void launch_scan_cov(const int32_t* diff, int32_t* cov, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st)
 {
     int tiles = scan_tiles_cov(n);
     if (tiles == 0) return;
@@ -200,7 +237,7 @@ void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ti
     cudaMemsetAsync(ticket, 0, sizeof(int), st);
     if (cs.tile_bytes)
         cudaMemcpyAsync(cs.tile_bytes, cs.tile_static, sizeof(int32_t) * (size_t)((n + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS), cudaMemcpyDeviceToDevice, st);
-    k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(data, n, status, ticket, cs);
+    k_scan_cov<<<tiles, CS_THREADS, 0, st>>>(diff, cov, n, status, ticket, cs);
 }
 
 // ---------------------------------------------------------------- scatter

@@ -77,18 +77,20 @@ void launch_read_layout(const int64_t* seq_off_local, int64_t m, int reso, int p
 // exclusive scan int32[n] -> int64[n+1]; tmp_status must hold scan_tiles(n) uint64 (+1 int ticket after it), zeroed by the launcher
 int  scan_tiles_small(int64_t n);
 void launch_scan_i32_to_i64(const int32_t* in, int64_t* out, int64_t n, uint64_t* status, int* ticket, cudaStream_t st);
-// in-place inclusive scan of the int32 difference array, fused with the sizing of coverage.txt (bytes per 1024-slot tile)
+// inclusive scan of the int32 difference array into the coverage array, fused with the sizing of coverage.txt (bytes per 1024-slot tile)
 constexpr int COV_TILE_SLOTS = 1024;
 struct CovSizeArgs {
     int32_t*       tile_bytes;  // null: scan only
     const int32_t* tile_static; // coverage-independent bytes of every tile (launch_cov_static_sizes); tile_bytes starts from it
+    const int64_t* slot_off;    // m+1
+    const int32_t* tile_read;   // read holding the first slot of every 1024-slot tile
 };
 // Coverage-independent part of coverage.txt per 1024-slot tile: "read i " prefixes, the digits of every bin position
 // (closed form per read and tile) and the sentinel newline, minus the 3 bytes the scan counts for a sentinel (whose
 // coverage is always 0).  The scan then only adds digits(cov) + 2 per slot.
 void launch_cov_static_sizes(const int64_t* slot_off, int64_t m, int64_t n_slots, int64_t own_first, int reso, int32_t* tile_static, cudaStream_t st);
 int  scan_tiles_cov(int64_t n);
-void launch_scan_cov_inplace(int32_t* data, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st);
+void launch_scan_cov(const int32_t* diff, int32_t* cov, int64_t n, uint64_t* status, int* ticket, const CovSizeArgs& cs, cudaStream_t st);
 
 struct ScatterArgs {
     const int32_t *qid, *tid, *qs, *qe, *ts, *te;

@@ -332,6 +332,33 @@ def test_many_tiny_reads_and_fragments():
     ctx.close()
 
 
+def test_reads_spanning_many_scan_tiles():
+    """The coverage scan derives a tile's incoming running sum from the read that spans the tile boundary; reads
+    longer than one 4096-slot scan tile take the chained path (tile waits for its predecessor).  Mix of reads of
+    0.3-1.2 Mbp at -r 10 (30 k-120 k slots each, up to 30 tiles per read) with short ones."""
+    rng = np.random.default_rng(17)
+    lens = [300000, 700, 1200000, 41000, 90, 450000, 5000, 40960, 40950, 40970]
+    names = [b"L%d" % i for i in range(len(lens))]
+    fa = b"".join(b">" + nm + b"\n" + bytes(rng.choice(list(b"ACGT"), int(L)).astype(np.uint8)) + b"\n" for nm, L in zip(names, lens))
+    reads = O.parse_fasta(fa)
+    lines = []
+    for _ in range(4000):
+        q, t = rng.integers(0, len(lens), 2)
+        if q == t:
+            continue
+        qs = int(rng.integers(0, lens[q])); qe = int(rng.integers(qs, lens[q] + 1))
+        ts = int(rng.integers(0, lens[t])); te = int(rng.integers(ts, lens[t] + 1))
+        lines.append(b"\t".join([names[q], b"%d" % lens[q], b"%d" % qs, b"%d" % qe, b"+", names[t], b"%d" % lens[t], b"%d" % ts, b"%d" % te,
+                                 b"9", b"9", b"60"]))
+    paf = b"\n".join(lines) + b"\n"
+    kw = dict(est_cov=150, reso=10, repeat_length=5000, read_length=20000, overlap_length=500, flanking_length=500)
+    ref = O.run(reads, paf, O.make_params(**kw))
+    assert ref.status == 0 and ref.symmetric == 0
+    ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
+    compare_all(ctx, st, ref)
+    ctx.close()
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_deferred_sequence_upload(pinned):
     """RAFTGPU_OPT_DEFER_SEQ_UPLOAD: the arena is uploaded in chunks behind the PAF; windows wait for their chunks."""
