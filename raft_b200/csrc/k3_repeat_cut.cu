@@ -33,12 +33,17 @@ __global__ void __launch_bounds__(K3_THREADS) k_repeat_cut(RepeatCutArgs a)
         c0 = __shfl_sync(FULL, c0, 0);
         if (c0 >= a.m) break;
         int64_t c1 = c0 + K3_CHUNK < a.m ? c0 + K3_CHUNK : a.m;
-        for (int64_t i = c0; i < c1; i++) {
-            const int64_t  L = a.seq_off[i + 1] - a.seq_off[i];
-            const int64_t  base = a.slot_off[i];
-            const int      nb = (int)(a.slot_off[i + 1] - base - 1);
+        // offsets of the chunk's reads: four coalesced loads for up to eight reads, handed out by shuffles
+        const int     cnt = (int)(c1 - c0);
+        const int64_t m_slot = lane <= cnt ? a.slot_off[c0 + lane] : 0, m_seq = lane <= cnt ? a.seq_off[c0 + lane] : 0;
+        const int64_t m_rep = lane < cnt ? a.rep_cap_off[c0 + lane] : 0, m_cut = lane < cnt ? a.cut_cap_off[c0 + lane] : 0;
+        for (int j = 0; j < cnt; j++) {
+            const int64_t  i = c0 + j;
+            const int64_t  L = __shfl_sync(FULL, m_seq, j + 1) - __shfl_sync(FULL, m_seq, j);
+            const int64_t  base = __shfl_sync(FULL, m_slot, j);
+            const int      nb = (int)(__shfl_sync(FULL, m_slot, j + 1) - base - 1);
             const int32_t* cov = a.cov + base;
-            int2*          rep = a.rep + a.rep_cap_off[i];
+            int2*          rep = a.rep + __shfl_sync(FULL, m_rep, j);
             int            nrep = 0;
             int            run_start = -1;
 
@@ -54,27 +59,42 @@ __global__ void __launch_bounds__(K3_THREADS) k_repeat_cut(RepeatCutArgs a)
                 }
             };
 
-            for (int k0 = 0; k0 < nb; k0 += 128) {
-                // four independent loads in flight per lane
-                int c[4];
+            int cn[4]; // next group's coverage, loaded one iteration ahead
 #pragma unroll
-                for (int u = 0; u < 4; u++) { int k = k0 + u * 32 + lane; c[u] = k < nb ? cov[k] : 0x80000000; }
+            for (int u = 0; u < 4; u++) { const int k = u * 32 + lane; cn[u] = k < nb ? cov[k] : 0; }
+            for (int k0 = 0; k0 < nb; k0 += 128) {
+                // four independent loads in flight per lane; bins past the read's end count as 0 and never set a mask bit
+                int      c[4];
+                unsigned m[4];
+                int      part = 0; // |cov| < 2^31 / 4 in any input whose record count fits an int
+#pragma unroll
+                for (int u = 0; u < 4; u++) c[u] = cn[u];
+                if (k0 + 128 < nb) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const int k = k0 + 128 + u * 32 + lane; cn[u] = k < nb ? cov[k] : 0; }
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    int kk = k0 + u * 32;
+                    const bool in = k0 + u * 32 + lane < nb;
+                    part += c[u];
+                    m[u] = __ballot_sync(FULL, in && c[u] >= a.H);
+                }
+                sum_cov += (unsigned long long)(long long)part;
+                if ((m[0] | m[1] | m[2] | m[3]) == 0u && run_start < 0) continue; // no bin at or above H here and no open run
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int kk = k0 + u * 32;
                     if (kk >= nb) break;
-                    bool in = (kk + lane) < nb;
-                    if (in) sum_cov += (unsigned long long)(long long)c[u];
-                    unsigned m = __ballot_sync(FULL, in && c[u] >= a.H);
-                    int      bit = 0;
+                    const unsigned mu = m[u]; // bins past nb have their bit clear, which closes a run that reaches the read's end at nb
+                    int            bit = 0;
                     while (bit < 32) {
                         if (run_start < 0) {
-                            unsigned mm = m & (0xFFFFFFFFu << bit);
+                            unsigned mm = mu & (0xFFFFFFFFu << bit);
                             if (!mm) break;
                             int s = __ffs(mm) - 1;
                             run_start = kk + s; bit = s + 1;
                         } else {
-                            unsigned inv = ~m & (0xFFFFFFFFu << bit);
+                            unsigned inv = ~mu & (0xFFFFFFFFu << bit);
                             if (!inv) break;
                             int e = __ffs(inv) - 1;
                             emit(run_start, kk + e);
@@ -90,7 +110,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_repeat_cut(RepeatCutArgs a)
             // stars and cuts
             const int64_t parts = L / a.P;
             const int     nstars = (int)(parts + 1 + (L % a.P != 0));
-            int32_t*      cuts = a.cuts + a.cut_cap_off[i];
+            int32_t*      cuts = a.cuts + __shfl_sync(FULL, m_cut, j);
             int           nf = 0;
             for (int j0 = 0; j0 < nstars; j0 += 32) {
                 int  j = j0 + lane;
