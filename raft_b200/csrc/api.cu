@@ -69,7 +69,10 @@ constexpr size_t WINDOW_BYTES = 256ull << 20; // staging window for host fetches
 
 struct raftgpu_ctx {
     int            device = 0;
-    cudaStream_t   st = nullptr, st2 = nullptr;
+    cudaStream_t   st = nullptr, st2 = nullptr, st_zero = nullptr;
+    cudaEvent_t    ev_scan_done = nullptr;
+    void*          diff_zero_ptr = nullptr; // difference array known to be all zero once st_zero has drained ...
+    int64_t        diff_zero_ints = 0;      // ... over this many leading ints
     raftgpu_params prm{};
     std::string    last_error;
     int64_t        err_index = -1;
@@ -221,6 +224,8 @@ int raftgpu_create(const raftgpu_params* p, int device, raftgpu_ctx** out)
     auto bail = [&](void) { delete ctx; return RAFTGPU_E_CUDA; };
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&ctx->st_zero, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaEventCreateWithFlags(&ctx->ev_scan_done, cudaEventDisableTiming) != cudaSuccess) return bail();
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail();
     for (auto& e : ctx->ev_stage) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess) return bail();
@@ -237,6 +242,8 @@ int raftgpu_destroy(raftgpu_ctx* ctx)
     if (!ctx) return RAFTGPU_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2);
+    if (ctx->st_zero) { cudaStreamSynchronize(ctx->st_zero); cudaStreamDestroy(ctx->st_zero); }
+    if (ctx->ev_scan_done) cudaEventDestroy(ctx->ev_scan_done);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
     for (auto& L : ctx->lane) { if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
@@ -789,8 +796,14 @@ static ScatterArgs scatter_args(raftgpu_ctx* ctx)
 static int zero_diff(raftgpu_ctx* ctx)
 {
     if (ctx->diff_zeroed) return RAFTGPU_OK;
+    CK(cudaStreamSynchronize(ctx->st_zero)); // a re-zeroing of the previous run may still be writing the old buffer
     CK(ctx->b_diff.ensure(sizeof(int32_t) * (size_t)(ctx->n_slots + 8)));
-    CK(cudaMemsetAsync(ctx->b_diff.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st));
+    if (ctx->diff_zero_ptr == ctx->b_diff.p && ctx->diff_zero_ints >= ctx->n_slots) {
+        // the previous run zeroed the array again right after its scan had consumed it (finalize), behind K3 and the emitters
+    } else {
+        CK(cudaMemsetAsync(ctx->b_diff.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st));
+    }
+    ctx->diff_zero_ints = 0;
     ctx->diff_zeroed = true;
     return RAFTGPU_OK;
 }
@@ -906,6 +919,13 @@ extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
     launch_repeat_cut(ra, ctx->st);
     CKL();
     cudaEventRecord(ctx->ev[5], ctx->st);
+    // the differences were consumed by the scan: zero them for the next run on a side stream, once K3 (latency-bound,
+    // it would feel the competition) is done -- the memset then runs beside the layout kernels and the issue-bound text
+    // emitter (measured: 76.5 -> 75.7 ms per pass; a thin persistent zeroing kernel instead of the memset gained less)
+    CK(cudaEventRecord(ctx->ev_scan_done, ctx->st));
+    CK(cudaStreamWaitEvent(ctx->st_zero, ctx->ev_scan_done, 0));
+    CK(cudaMemsetAsync(ctx->b_diff.p, 0, sizeof(int32_t) * (size_t)ctx->n_slots, ctx->st_zero));
+    ctx->diff_zero_ptr = ctx->b_diff.p; ctx->diff_zero_ints = ctx->n_slots;
     // fragment numbering inside this context
     CK(ctx->b_frag_base.ensure(sizeof(int64_t) * (size_t)(m + 1)));
     launch_scan_i32_to_i64(ctx->b_frag_cnt.as<int32_t>(), ctx->b_frag_base.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &M->ticket, ctx->st);
