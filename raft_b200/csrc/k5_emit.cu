@@ -129,12 +129,19 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
         return v;
     };
     int  ro = 0; // text offset of the chunk inside the tile
-    int4 cvn = load4(CW_PER * lane);
+    constexpr int NQ = CW_PER / 4;
+    int4 cvn[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) cvn[q] = load4(CW_PER * lane + 4 * q);
     for (int sl0 = 0; sl0 < nvalid; sl0 += CW_CHUNK) {
         const int  s0 = sl0 + CW_PER * lane;
-        const int4 cq = cvn;
-        if (sl0 + CW_CHUNK < nvalid) cvn = load4(s0 + CW_CHUNK);
-        const int cv[CW_PER] = {cq.x, cq.y, cq.z, cq.w};
+        int cv[CW_PER];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) { cv[4 * q] = cvn[q].x; cv[4 * q + 1] = cvn[q].y; cv[4 * q + 2] = cvn[q].z; cv[4 * q + 3] = cvn[q].w; }
+        if (sl0 + CW_CHUNK < nvalid) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) cvn[q] = load4(s0 + CW_CHUNK + 4 * q);
+        }
         // read of this lane's first slot
         int        lrs = rs, lre = re, lmr = mr;
         const bool crossing = sl0 + CW_CHUNK - 1 >= re - 1; // the chunk reaches this read's sentinel
