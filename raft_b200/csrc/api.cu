@@ -58,6 +58,7 @@ struct Misc {
     unsigned long long stats[2];
     unsigned long long digest;
     unsigned long long route_counts[64];
+    unsigned long long route_list_n;
     int                fa_flags;
     int                fa_pad;
     long long          fa_totals[2];
@@ -104,6 +105,7 @@ struct raftgpu_ctx {
 
     // coverage + K3 + layout
     DevBuf  b_cov, b_diff; bool diff_zeroed = false, finalized = false, sized = false;
+    DevBuf  b_bounds, b_route_list; int64_t route_collected = -1; // endpoints in b_route_list (-1: list incomplete)
     DevBuf  b_rep, b_rep_cnt, b_cuts, b_frag_cnt, b_frag_base;
     DevBuf  b_frag_read, b_frag_a, b_frag_b, b_frag_size, b_frag_off;
     DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_static, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
@@ -850,19 +852,28 @@ extern "C" int raftgpu_accumulate_endpoints(raftgpu_ctx* ctx, const void* ep, in
     return RAFTGPU_OK;
 }
 
+constexpr unsigned long long ROUTE_LIST_CAP = 4ull << 20; // collected endpoints (16 B each); more: two-pass packing
+
 extern "C" int raftgpu_route_count(raftgpu_ctx* ctx, int nranks, const int64_t* bounds, int64_t* counts)
 {
     if (!ctx || nranks < 1 || nranks > 64 || !bounds || !counts) return RAFTGPU_E_ARG;
     if (!ctx->paf_done) FAIL(RAFTGPU_E_STATE, "raftgpu_route_count: finish PAF ingest first");
     CK(cudaSetDevice(ctx->device));
-    DevBuf db;
-    CK(db.ensure(sizeof(int64_t) * (nranks + 1)));
-    CK(cudaMemcpyAsync(db.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemsetAsync(ctx->misc()->route_counts, 0, sizeof(unsigned long long) * 64, ctx->st));
-    launch_route_count(scatter_args(ctx), nranks, db.as<int64_t>(), ctx->misc()->route_counts, ctx->st);
+    Misc* M = ctx->misc();
+    CK(ctx->b_bounds.ensure(sizeof(int64_t) * 65));
+    CK(ctx->b_route_list.ensure(sizeof(int4) * ROUTE_LIST_CAP));
+    CK(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(M->route_counts, 0, sizeof(unsigned long long) * 65, ctx->st)); // counts and the list cursor behind them
+    unsigned long long cap = ROUTE_LIST_CAP;
+    if (const char* e = getenv("RAFT_B200_ROUTE_CAP")) { long long v = atoll(e); if (v >= 0 && (unsigned long long)v < cap) cap = (unsigned long long)v; } // test knob: force the two-pass packing
+    launch_route_collect(scatter_args(ctx), nranks, ctx->b_bounds.as<int64_t>(), M->route_counts, ctx->b_route_list.as<int4>(), &M->route_list_n,
+                         cap, ctx->st);
     CKL();
-    CK(cudaMemcpyAsync(counts, ctx->misc()->route_counts, sizeof(int64_t) * nranks, cudaMemcpyDeviceToHost, ctx->st));
+    unsigned long long h[65];
+    CK(cudaMemcpyAsync(h, M->route_counts, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
+    for (int r = 0; r < nranks; r++) counts[r] = (int64_t)h[r];
+    ctx->route_collected = h[64] <= cap ? (int64_t)h[64] : -1;
     return RAFTGPU_OK;
 }
 
@@ -870,14 +881,19 @@ extern "C" int raftgpu_route_pack(raftgpu_ctx* ctx, int nranks, const int64_t* b
 {
     if (!ctx || nranks < 1 || nranks > 64 || !bounds || !counts) return RAFTGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    DevBuf db;
-    CK(db.ensure(sizeof(int64_t) * (nranks + 1)));
-    CK(cudaMemcpyAsync(db.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
+    Misc* M = ctx->misc();
     unsigned long long cur[64] = {0};
     for (int r = 1; r < nranks; r++) cur[r] = cur[r - 1] + (unsigned long long)counts[r - 1];
-    CK(cudaMemcpyAsync(ctx->misc()->route_counts, cur, sizeof cur, cudaMemcpyHostToDevice, ctx->st));
-    launch_route_pack(scatter_args(ctx), nranks, db.as<int64_t>(), ctx->misc()->route_counts, (int32_t*)sendbuf, ctx->st);
+    CK(cudaMemcpyAsync(M->route_counts, cur, sizeof cur, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->route_collected >= 0) { // the count pass kept every endpoint: bucket the short list
+        launch_route_pack_list(ctx->b_route_list.as<int4>(), ctx->route_collected, M->route_counts, (int32_t*)sendbuf, ctx->st);
+    } else {
+        CK(ctx->b_bounds.ensure(sizeof(int64_t) * 65));
+        CK(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(int64_t) * (nranks + 1), cudaMemcpyHostToDevice, ctx->st));
+        launch_route_pack(scatter_args(ctx), nranks, ctx->b_bounds.as<int64_t>(), M->route_counts, (int32_t*)sendbuf, ctx->st);
+    }
     CKL();
+    ctx->route_collected = -1;
     CK(cudaStreamSynchronize(ctx->st));
     return RAFTGPU_OK;
 }

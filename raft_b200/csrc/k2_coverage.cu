@@ -339,11 +339,69 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
     }
     }
 }
+// Count pass that also collects: blocks that saw an endpoint for another rank reserve a range of the bounded list with one
+// atomic and write (read, start, end, destination) there, so that packing only touches the collected endpoints -- with
+// query-grouped symmetric PAF they are a few thousand out of 10^8 records.  counters[0..nranks) = endpoints per destination,
+// *list_n = endpoints collected (may exceed cap: then the list is incomplete and the caller packs with k_route<true>).
+__global__ void __launch_bounds__(256) k_route_collect(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
+                                                       int4* list, unsigned long long* list_n, unsigned long long cap)
+{
+    extern __shared__ unsigned long long s_cnt[]; // nranks block-local counts, then [nranks] = block total / cursor, [nranks+1] = base
+    const bool sym = *a.sym_flag != 0;
+    for (int r = threadIdx.x; r < nranks + 2; r += blockDim.x) s_cnt[r] = 0;
+    __syncthreads();
+    // a block owns a contiguous chunk of records (a multiple of 1024, so 128-bit loads of the id columns stay aligned)
+    const int64_t per = (((a.n_rec + gridDim.x - 1) / gridDim.x) + 1023) & ~(int64_t)1023;
+    const int64_t k0 = (int64_t)blockIdx.x * per, k1 = k0 + per < a.n_rec ? k0 + per : a.n_rec;
+    const int64_t own_lo = a.own_first, own_hi = a.own_first + a.own_count;
+    auto count_one = [&](int q, int t) {
+        if (q < own_lo || q >= own_hi) { atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull); atomicAdd(&s_cnt[nranks], 1ull); }
+        if (!sym && t != q && (t < own_lo || t >= own_hi)) { atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull); atomicAdd(&s_cnt[nranks], 1ull); }
+    };
+    for (int64_t k = k0 + 4 * (int64_t)threadIdx.x; k < k1; k += 4 * (int64_t)blockDim.x) {
+        if (k + 4 <= k1) { // four records per thread and iteration: two 128-bit loads in flight
+            const int4 q4 = *reinterpret_cast<const int4*>(a.qid + k), t4 = *reinterpret_cast<const int4*>(a.tid + k);
+            count_one(q4.x, t4.x); count_one(q4.y, t4.y); count_one(q4.z, t4.z); count_one(q4.w, t4.w);
+        } else {
+            for (int64_t j = k; j < k1; j++) count_one(a.qid[j], a.tid[j]);
+        }
+    }
+    __syncthreads();
+    const unsigned long long total = s_cnt[nranks];
+    if (total == 0) return;
+    for (int r = threadIdx.x; r < nranks; r += blockDim.x)
+        if (s_cnt[r]) atomicAdd(&counters[r], s_cnt[r]);
+    if (threadIdx.x == 0) { s_cnt[nranks + 1] = atomicAdd(list_n, total); s_cnt[nranks] = 0; }
+    __syncthreads();
+    const unsigned long long base = s_cnt[nranks + 1];
+    if (base + total > cap) return; // the list cannot hold this block's endpoints: the caller falls back to the two-pass packing
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        int q = a.qid[k], t = a.tid[k];
+        if (q < own_lo || q >= own_hi)
+            list[base + atomicAdd(&s_cnt[nranks], 1ull)] = make_int4(q, a.qs[k], a.qe[k], owner_of(bounds, nranks, q));
+        if (!sym && t != q && (t < own_lo || t >= own_hi))
+            list[base + atomicAdd(&s_cnt[nranks], 1ull)] = make_int4(t, a.ts[k], a.te[k], owner_of(bounds, nranks, t));
+    }
+}
+// buckets the collected endpoints by destination: cursors[d] = first free endpoint slot of destination d in sendbuf
+__global__ void __launch_bounds__(256) k_route_pack_list(const int4* __restrict__ list, int64_t n, unsigned long long* cursors, int32_t* sendbuf)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int4               e = list[k];
+    const unsigned long long slot = atomicAdd(&cursors[e.w], 1ull);
+    sendbuf[3 * slot] = e.x; sendbuf[3 * slot + 1] = e.y; sendbuf[3 * slot + 2] = e.z;
+}
 static unsigned route_blocks(int64_t n) { int64_t b = (n + 4095) / 4096; if (b < 1) b = 1; if (b > 148 * 8) b = 148 * 8; return (unsigned)b; }
-void launch_route_count(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* counts, cudaStream_t st)
+void launch_route_collect(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* counts, int4* list,
+                          unsigned long long* list_n, unsigned long long cap, cudaStream_t st)
 {
     if (a.n_rec <= 0) return;
-    k_route<false><<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, counts, nullptr);
+    k_route_collect<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * (nranks + 2), st>>>(a, nranks, bounds, counts, list, list_n, cap);
+}
+void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
+{
+    if (n > 0) k_route_pack_list<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(list, n, cursors, sendbuf);
 }
 void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
 {

@@ -108,7 +108,11 @@ void launch_scatter_records(const ScatterArgs& a, cudaStream_t st);
 void launch_scatter_endpoints(const int32_t* ep, int64_t n, const int64_t* slot_off, int32_t* diff, int reso, int64_t own_first,
                               int64_t own_count, ErrState* err, cudaStream_t st);
 // multi-GPU routing
-void launch_route_count(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* counts_dev, cudaStream_t st);
+// count endpoints per destination rank and collect them (id, start, end, destination) into a bounded list; *list_n > cap
+// means the list is incomplete and launch_route_pack (a second pass over the records) must be used
+void launch_route_collect(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* counts_dev, int4* list,
+                          unsigned long long* list_n, unsigned long long cap, cudaStream_t st);
+void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cursors_dev, int32_t* sendbuf, cudaStream_t st);
 void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* cursors_dev, int32_t* sendbuf,
                        cudaStream_t st);
 

@@ -92,9 +92,20 @@ class TorchComm:
 def run_rank(engine, comm, bounds, text, nbytes):
     """Steps 1-4 for one rank.  Returns (stats, info dict)."""
     rank, world = comm.rank, comm.world
+    import time
+    tm, t_last = {}, time.perf_counter()
+
+    def lap(name):  # host wall time of each protocol phase (every phase ends in a host-visible result)
+        nonlocal t_last
+        now = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + (now - t_last) * 1e3
+        t_last = now
+
     # -- record 0 of the whole file
     rec, found = engine.peek_first_record(text, nbytes)
+    lap("peek")
     allrec = comm.all_gather_i64([1 if found else 0] + list(rec))
+    lap("gather_rec0")
     holders = [r for r in range(world) if allrec[r][0]]
     if holders:
         h = holders[0]
@@ -103,26 +114,33 @@ def run_rank(engine, comm, bounds, text, nbytes):
         engine.set_first_record(None, is_local=False)
     # -- tokenise the local byte range
     engine.ingest_paf(text, nbytes, last=True)
+    lap("tokenize")
     # -- symmetric flag: OR over ranks
     sym = int(comm.all_gather_i64([engine.get_symmetric()]).max())
     engine.set_symmetric(sym)
+    lap("gather_sym")
     # -- intervals on reads this rank owns are scattered directly; the rest is routed to the owners
     engine.accumulate_local()
     counts = engine.route_count(bounds)
+    lap("route_count")
     recv_counts = comm.all_to_all_counts(counts)
+    lap("a2a_counts")
     send = comm.alloc_i32(3 * int(counts.sum()))
     engine.route_pack(bounds, counts, send)
     recv = comm.alloc_i32(3 * int(recv_counts.sum()))
     comm.all_to_all_v(recv, send, 3 * recv_counts, 3 * counts)
+    lap("a2a_data")
     engine.accumulate_endpoints(recv, int(recv_counts.sum()))
     # -- local coverage / repeats / cut points, then global numbering
     st = engine.finalize()
+    lap("finalize")
     per_rank = comm.all_gather_i64([int(st.n_fragments), int(st.n_records)])
     first_num = 1 + int(per_rank[:rank, 0].sum())
     engine.set_output_base(first_num)
+    lap("gather_frags")
     info = dict(symmetric=sym, sent=int(counts.sum()), received=int(recv_counts.sum()), first_read_num=first_num,
                 n_records_total=int(per_rank[:, 1].sum()), n_fragments_total=int(per_rank[:, 0].sum()),
-                sent_remote=int(counts.sum()))
+                sent_remote=int(counts.sum()), phase_ms=tm)
     return st, info
 
 
@@ -244,6 +262,7 @@ def bench(a, rank, world, local, log):
                                        "collective": "all_to_all_single (NCCL) of 12-byte endpoints + counts"},
                           "l2": "inputs and outputs are GBs per rank (>> 126 MB L2); no explicit flush"},
                "gbp_per_s": int(tot[:, 2].sum()) / (ms / 1e3) / 1e9, "stage_ms_rank0": stage,
+               "protocol_ms_rank0": {k: round(v, 3) for k, v in info["phase_ms"].items()},
                "roofline": {"kernel": "k_fasta_emit", "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
                             "achieved": None if not fasta_ms else fasta_alg / (fasta_ms / 1e3) / 1e9,
                             "frac": None if not fasta_ms else fasta_alg / (fasta_ms / 1e3) / 1e9 / peak,

@@ -18,15 +18,20 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("cfg,scale,sym,world", [("C1", 0.2, False, 2), ("C1", 0.2, True, 2), ("C5", 0.003, False, 3), ("C4", 0.002, False, 2)])
-def test_sharded_cuda_matches_oracle(cfg, scale, sym, world):
+@pytest.mark.parametrize("cfg,scale,sym,world,route_cap", [("C1", 0.2, False, 2, None), ("C1", 0.2, True, 2, None), ("C5", 0.003, False, 3, None),
+                                                           ("C4", 0.002, False, 2, None), ("C1", 0.2, False, 2, 64)])
+def test_sharded_cuda_matches_oracle(cfg, scale, sym, world, route_cap):
+    """route_cap: RAFT_B200_ROUTE_CAP forces the two-pass packing (endpoint list overflow) instead of the collected list."""
     ngpu = torch.cuda.device_count()
     backend = "nccl" if ngpu >= world else "gloo"
     port = 29600 + (os.getpid() % 2000)
     with tempfile.TemporaryDirectory() as d:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                "--master-port", str(port), os.path.join(HERE, "mgpu_worker.py"), cfg, str(scale), "1" if sym else "0", d, backend]
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+        env = dict(os.environ)
+        if route_cap is not None:
+            env["RAFT_B200_ROUTE_CAP"] = str(route_cap)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, env=env)
         assert r.returncode == 0, r.stdout.decode()[-4000:]
         outs = [torch.load(os.path.join(d, f"r{k}.pt"), weights_only=False) for k in range(world)]
     ds = synth.make_dataset(cfg, scale, sym, seed=99)
