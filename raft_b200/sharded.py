@@ -65,10 +65,9 @@ class TorchComm:
         return np.stack([o.cpu().numpy() for o in out])
 
     def all_to_all_counts(self, counts):
-        t = self.torch.tensor(np.asarray(counts, dtype=np.int64), device=self.device)
-        out = self.torch.empty_like(t)
-        self.dist.all_to_all_single(out, t)
-        return out.cpu().numpy()
+        """counts[d] = endpoints this rank sends to d; returns what every rank sends to this one.  An all-gather of the
+        rows (the whole matrix is tiny) is one collective with a ring/tree schedule instead of world point-to-point pairs."""
+        return self.all_gather_i64([int(c) for c in counts])[:, self.rank].astype(np.int64)
 
     def alloc_i32(self, n):
         return self.torch.empty(max(int(n), 1), dtype=self.torch.int32, device=self.buf_device)
