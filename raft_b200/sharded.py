@@ -57,9 +57,18 @@ class TorchComm:
         self.dist, self.device, self.torch = dist, device, torch
         self.buf_device = device if buf_device is None else buf_device
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self._flat_gather = True
 
     def all_gather_i64(self, vals):
+        """world x len(vals) int64 matrix; one flat output tensor and one device-to-host copy."""
         t = self.torch.tensor(list(vals), dtype=self.torch.int64, device=self.device)
+        if self._flat_gather:
+            try:
+                out = self.torch.empty(self.world * t.numel(), dtype=self.torch.int64, device=self.device)
+                self.dist.all_gather_into_tensor(out, t)
+                return out.cpu().numpy().reshape(self.world, -1)
+            except (RuntimeError, NotImplementedError):  # backend without the flat variant
+                self._flat_gather = False
         out = [self.torch.empty_like(t) for _ in range(self.world)]
         self.dist.all_gather(out, t)
         return np.stack([o.cpu().numpy() for o in out])
