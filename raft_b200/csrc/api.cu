@@ -361,7 +361,7 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
     // per-read slot / capacity layout (three exclusive scans)
     CK(ctx->b_slots.ensure(sizeof(int32_t) * (m + 1))); CK(ctx->b_repcap.ensure(sizeof(int32_t) * (m + 1)));
     CK(ctx->b_cutcap.ensure(sizeof(int32_t) * (m + 1)));
-    CK(ctx->b_slot_off.ensure(sizeof(int64_t) * (m + 1))); CK(ctx->b_rep_cap_off.ensure(sizeof(int64_t) * (m + 1)));
+    CK(ctx->b_slot_off.ensure(sizeof(int64_t) * (m + 2))); CK(ctx->b_rep_cap_off.ensure(sizeof(int64_t) * (m + 1)));
     CK(ctx->b_cut_cap_off.ensure(sizeof(int64_t) * (m + 1)));
     CK(ctx->b_status.ensure(sizeof(uint64_t) * (scan_tiles_small(m) + 8)));
     launch_read_layout(ctx->d_seq_off, m, P.reso, P.repeat_length, P.interval_length, P.read_length, ctx->b_slots.as<int32_t>(),
@@ -369,6 +369,10 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
     CKL();
     launch_scan_i32_to_i64(ctx->b_slots.as<int32_t>(), ctx->b_slot_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);
     CKL();
+    {   // one entry past the end: the coverage.txt emitter steps to "the read after the last one" without a bounds test
+        static const int64_t past_end = (int64_t)1 << 62;
+        CK(cudaMemcpyAsync(ctx->b_slot_off.as<int64_t>() + m + 1, &past_end, sizeof past_end, cudaMemcpyHostToDevice, ctx->st));
+    }
     launch_scan_i32_to_i64(ctx->b_repcap.as<int32_t>(), ctx->b_rep_cap_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);
     CKL();
     launch_scan_i32_to_i64(ctx->b_cutcap.as<int32_t>(), ctx->b_cut_cap_off.as<int64_t>(), m, ctx->b_status.as<uint64_t>(), &ctx->misc()->ticket, ctx->st);

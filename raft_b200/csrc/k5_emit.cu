@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
     // everything inside the tile is 32-bit and relative: slots to g0, text bytes to oc0
     constexpr int FAR = 1 << 20;
     auto rel = [&](int64_t slot) { const int64_t d = slot - g0; return d > FAR ? FAR : (int)d; }; // a read has < 2^31 slots
+    // slot_off carries one entry past the end (2^62), so stepping past the last read's sentinel needs no bounds test
     int            rs = rel(a.slot_off[r]), re = rel(a.slot_off[r + 1]), mr = 0; // warp-uniform: read of the chunk's first slot (= r + mr)
     const int      nvalid = a.n_slots - g0 < COV_TILE_SLOTS ? (int)(a.n_slots - g0) : COV_TILE_SLOTS;
     const int64_t  dlo = a.w0 - oc0, dhi = a.w1 - oc0;

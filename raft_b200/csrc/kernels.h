@@ -183,7 +183,7 @@ void launch_rep_compact(const int32_t* rep_cnt, const int64_t* rep_cap_off, cons
 // ---------------------------------------------------------------- K5 (k5_emit.cu)
 struct CovEmitArgs {
     const int32_t* cov;      // scanned slots
-    const int64_t* slot_off; // m+1
+    const int64_t* slot_off; // m+2: [m] = n_slots, [m+1] = 2^62 (lets the emitter step past the last read)
     int64_t        m, n_slots;
     int64_t        own_first; // global id of local read 0
     int            reso;
