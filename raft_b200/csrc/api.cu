@@ -121,7 +121,6 @@ struct raftgpu_ctx {
     // lane 0 (stream st_aux): coverage.txt, long_repeats.txt, .bed;  lane 1 (stream st): reads.fasta, split_naive
     struct EmitLane { cudaStream_t st = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool open = false; int kind = 0; };
     EmitLane     lane[2];
-    bool         emit_shared_gpu = false; // asynchronous emission: leave SM slots for the other lane
     cudaStream_t st_aux = nullptr;
 
     // split_naive stream (raftgpu_split_naive)
@@ -1124,9 +1123,8 @@ static void lane_flush(raftgpu_ctx* ctx, int li)
 }
 static void flush_emit_timer(raftgpu_ctx* ctx) { lane_flush(ctx, 0); lane_flush(ctx, 1); }
 // launch the emitter of stream `which` for bytes [w0, w1) on its lane's CUDA stream (no host synchronisation)
-static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d, bool shared_gpu = false)
+static int emit_window(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1, uint8_t* d)
 {
-    ctx->emit_shared_gpu = shared_gpu;
     if (w1 <= w0) return RAFTGPU_OK;
     const int li = lane_of(which), kind = which > 3 ? 3 : which; // the split_naive stream is accounted with the gather kernel
     auto&     L = ctx->lane[li];
@@ -1327,7 +1325,7 @@ extern "C" int raftgpu_fetch_async(raftgpu_ctx* ctx, int which, uint64_t off, ui
     if (!n) return RAFTGPU_OK;
     if (!is_device_ptr(dst_device)) FAIL(RAFTGPU_E_ARG, "raftgpu_fetch_async needs a device destination");
     CK(cudaSetDevice(ctx->device));
-    return emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst_device, true);
+    return emit_window(ctx, which, (int64_t)off, (int64_t)(off + n), dst_device);
 }
 
 extern "C" int raftgpu_sync(raftgpu_ctx* ctx)

@@ -293,9 +293,10 @@ __device__ __forceinline__ int owner_of(const int64_t* __restrict__ bounds, int 
     return lo;
 }
 
-template <bool PACK>
-__global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
-                                               int32_t* sendbuf)
+// Two-pass packing straight from the records (used when the collected list of k_route_collect overflowed): every block
+// counts its chunk's endpoints per destination, reserves a range per destination, then writes.
+__global__ void __launch_bounds__(256) k_route_pack(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
+                                                    int32_t* sendbuf)
 {
     extern __shared__ unsigned long long s_cnt[]; // nranks block-local counts, then nranks block bases
     const bool sym = *a.sym_flag != 0;
@@ -313,11 +314,6 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
         if (!sym && t != q && (t < own_lo || t >= own_hi)) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
     }
     __syncthreads();
-    if constexpr (!PACK) {
-        for (int r = threadIdx.x; r < nranks; r += blockDim.x)
-            if (s_cnt[r]) atomicAdd(&counters[r], s_cnt[r]);
-        return;
-    } else {
     // pass 2: reserve a range per destination, then write
     for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
         s_cnt[nranks + r] = s_cnt[r] ? atomicAdd(&counters[r], s_cnt[r]) : 0ull;
@@ -337,12 +333,11 @@ __global__ void __launch_bounds__(256) k_route(ScatterArgs a, int nranks, const 
             sendbuf[3 * slot] = t; sendbuf[3 * slot + 1] = a.ts[k]; sendbuf[3 * slot + 2] = a.te[k];
         }
     }
-    }
 }
 // Count pass that also collects: blocks that saw an endpoint for another rank reserve a range of the bounded list with one
 // atomic and write (read, start, end, destination) there, so that packing only touches the collected endpoints -- with
 // query-grouped symmetric PAF they are a few thousand out of 10^8 records.  counters[0..nranks) = endpoints per destination,
-// *list_n = endpoints collected (may exceed cap: then the list is incomplete and the caller packs with k_route<true>).
+// *list_n = endpoints collected (may exceed cap: then the list is incomplete and the caller packs with k_route_pack).
 __global__ void __launch_bounds__(256) k_route_collect(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
                                                        int4* list, unsigned long long* list_n, unsigned long long cap)
 {
@@ -406,7 +401,7 @@ void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cur
 void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
 {
     if (a.n_rec <= 0) return;
-    k_route<true><<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
+    k_route_pack<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
 }
 
 } // namespace raftk
