@@ -7,6 +7,7 @@ import tempfile
 import numpy as np
 import pytest
 
+from fuzz_util import fuzz_case
 from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
 from oracle import oracle as O
 from raft_b200 import api, synth
@@ -238,6 +239,25 @@ def test_async_fetch_lanes():
         assert bufs[w][:len(d)].cpu().numpy().tobytes() == d, w
         assert int(bufs[w][len(d):].sum()) == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzz_cuda_matches_oracle(block):
+    """The 150 random small inputs of tests/fuzz_util.py (zero-length intervals, reads shorter than a bin, lengths that
+    are multiples of -r / -p, mirrored first record, junk lines, CR LF, empty PAF): every table and every output byte."""
+    for seed in range(block * 50, block * 50 + 50):
+        fa, paf, args = fuzz_case(seed)
+        reads = O.parse_fasta(fa)
+        kw = args_to_kw(args)
+        ref = O.run(reads, paf, O.make_params(**kw))
+        assert ref.status == 0
+        ctx, st = gpu_run(reads, paf, api.AlgoParams(**kw))
+        try:
+            compare_all(ctx, st, ref)
+        except AssertionError as e:
+            raise AssertionError(f"fuzz seed {seed} args {args}: {e}") from e
+        finally:
+            ctx.close()
 
 
 def _stress_paf(ds, seed=0):
