@@ -154,8 +154,10 @@ def reference_arm(a):
         out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/u8",
                "data": "synthetic",
-               "config": {"workload": f"{a.config} human 32x ONT-Duplex-shaped reads + symmetric PAF, bounded sample (genome scale {scale:.4g}) "
-                                      f"file->file", "n_overlaps": n_ovl, "n_reads": reads.n, "bases": int(reads.seq_off[-1]), "flags": " ".join(args)},
+               "config": {"workload": f"{a.config} synthetic human 32x ONT-Duplex-shaped reads + symmetric all-vs-all PAF, genome scale {a.scale:g} "
+                                      f"(raft {' '.join(args)}, defaults -r 50 -l 20000): the workload of the default arm, timed on a bounded sample",
+                          "sample": f"the same generator at genome scale {scale:.4g}, file to file",
+                          "n_overlaps": n_ovl, "n_reads": reads.n, "bases": int(reads.seq_off[-1]), "flags": " ".join(args)},
                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
                                 "sample": f"{n_ovl} overlaps / {int(reads.seq_off[-1])} bases, file to file, wall clock around the process"},
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
