@@ -122,12 +122,13 @@ int raftgpu_set_option(raftgpu_ctx *ctx, int option, int64_t value);
 int raftgpu_set_reads(raftgpu_ctx *ctx, int64_t n, const int64_t *seq_off, const uint8_t *seq,
                       const int64_t *name_off, const uint8_t *names);
 
-/* Device FASTA ingest: the same records as loadFASTA / kseq_read (chop.hpp:88-131, kseq.h:240-298) cut
- * out of plain FASTA text by a CUDA kernel.  Call with consecutive chunks of the (inflated) file, chunks need not end
+/* Device FASTA / FASTQ ingest: the same records as loadFASTA / kseq_read (chop.hpp:88-131,
+ * kseq.h:240-298) cut out of plain FASTA text (any line wrapping) or strict four-line FASTQ text by a CUDA kernel.  Call with consecutive chunks of the (inflated) file, chunks need not end
  * on newlines, last_chunk=1 on the final one (which also builds the layout and the name table, like
  * raftgpu_set_reads).  total_bytes_hint = size of the whole file if known (sizes the arena once), else 0.
- * Returns RAFTGPU_E_UNSUPPORTED — and leaves the context reset — for input the kernel does not take: FASTQ, CR LF
- * line ends, text that does not start with '>' or '@'; use raftgpu_load_fasta + raftgpu_set_reads then.  [host|device] */
+ * Returns RAFTGPU_E_UNSUPPORTED — and leaves the context reset — for input the kernel does not take: FASTQ with
+ * wrapped or truncated sequence / quality lines, a '+' line in FASTA, CR LF line ends, text that does not start with
+ * '>' or '@'; use raftgpu_load_fasta + raftgpu_set_reads then.  [host|device] */
 int raftgpu_ingest_fasta(raftgpu_ctx *ctx, const uint8_t *text, size_t nbytes, int last_chunk, uint64_t total_bytes_hint);
 
 /* Host FASTA/FASTQ(+gz) reader with kseq_read semantics (kseq.h:240-298); arrays are malloc'd and

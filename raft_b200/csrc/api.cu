@@ -61,7 +61,7 @@ struct Misc {
     unsigned long long route_list_n;
     int                fa_flags;
     int                fa_pad;
-    long long          fa_totals[2];
+    long long          fa_totals[3];
 };
 
 constexpr size_t WINDOW_BYTES = 256ull << 20; // staging window for host fetches
@@ -132,8 +132,11 @@ struct raftgpu_ctx {
     // device FASTA ingest (raftgpu_ingest_fasta)
     bool    fasta_active = false;
     int64_t fa_n = 0, fa_bases = 0, fa_name_bytes = 0, fa_rec_cap = 0;
+    bool    fa_fastq = false;                         // strict four-line FASTQ mode of the device tokenizer
+    int64_t fa_lines = 0, fa_text_bytes = 0, fa_gcap = 0; // lines / text bytes of the chunks so far; capacity of the per-record file offsets
+    bool    fa_ends_nl = true, fa_mode_known = false; // the FASTA / FASTQ decision needs the first three lines
     std::vector<uint8_t> fa_carry;
-    DevBuf  b_fa_text, b_fa_rec_pos, b_fa_name_len, b_fa_name_off_chunk, b_fa_status;
+    DevBuf  b_fa_text, b_fa_rec_pos, b_fa_name_len, b_fa_name_off_chunk, b_fa_status, b_fa_rec_gpos, b_fa_qual_gpos;
 
     // deferred sequence upload (RAFTGPU_OPT_DEFER_SEQ_UPLOAD)
     bool           opt_defer_seq = false;
@@ -271,6 +274,7 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
     ctx->q_scattered = false; ctx->h_sym = 0;
     ctx->fasta_active = false; ctx->fa_n = ctx->fa_bases = ctx->fa_name_bytes = 0; ctx->fa_carry.clear();
+    ctx->fa_fastq = false; ctx->fa_lines = ctx->fa_text_bytes = 0; ctx->fa_ends_nl = true; ctx->fa_mode_known = false;
     ctx->sn_len = 0; ctx->sn_G = 0; ctx->sn_bytes = 0;
     ctx->G = ctx->n_repeats = ctx->read_num_base = 0; ctx->launches = 0; ctx->err_index = -1;
     ctx->stats = raftgpu_stats{};
@@ -503,7 +507,7 @@ static int fasta_chunk(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len, bool
     if (len <= 0) return RAFTGPU_OK;
     Misc*     M = ctx->misc();
     const int tiles = fasta_tokenize_tiles(len);
-    CK(ctx->b_fa_status.ensure(sizeof(uint64_t) * 3 * (size_t)(tiles + 8)));
+    CK(ctx->b_fa_status.ensure(sizeof(uint64_t) * 4 * (size_t)(tiles + 8)));
     CK(ctx->b_seq.ensure((size_t)(ctx->fa_bases + len) + 64, (size_t)ctx->fa_bases, ctx->st)); // arena: at most one byte per text byte
     int64_t want_cap = len / 512 + 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -514,22 +518,30 @@ static int fasta_chunk(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len, bool
             CK(ctx->b_name_off.ensure(sizeof(int64_t) * (size_t)(cap + 1), sizeof(int64_t) * (size_t)ctx->fa_n, ctx->st));
             ctx->fa_rec_cap = cap;
         }
+        if (ctx->fa_fastq && need + 2 > ctx->fa_gcap) { // file offsets of every record's '@' and quality line (index = line / 4)
+            const int64_t cap = need + need / 4 + 2, keep = sizeof(int64_t) * (size_t)std::min<int64_t>(ctx->fa_gcap, ctx->fa_n + 2);
+            CK(ctx->b_fa_rec_gpos.ensure(sizeof(int64_t) * (size_t)cap, (size_t)keep, ctx->st));
+            CK(ctx->b_fa_qual_gpos.ensure(sizeof(int64_t) * (size_t)cap, (size_t)keep, ctx->st));
+            ctx->fa_gcap = cap;
+        }
         CK(ctx->b_fa_rec_pos.ensure(sizeof(int64_t) * (size_t)(want_cap + 1)));
-        CK(cudaMemsetAsync(ctx->b_fa_status.p, 0, sizeof(uint64_t) * 3 * (size_t)tiles, ctx->st));
+        CK(cudaMemsetAsync(ctx->b_fa_status.p, 0, sizeof(uint64_t) * 4 * (size_t)tiles, ctx->st));
         CK(cudaMemsetAsync(&M->ticket, 0, sizeof(int), ctx->st));
-        CK(cudaMemsetAsync(&M->fa_flags, 0, sizeof(int) * 2 + sizeof(long long) * 2, ctx->st));
+        CK(cudaMemsetAsync(&M->fa_flags, 0, sizeof(int) * 2 + sizeof(long long) * 3, ctx->st));
         FastaTokArgs a{};
         a.text = dtext; a.nbytes = len; a.n_tiles = tiles; a.first_chunk = first; a.last_chunk = last;
         a.seq_out = ctx->b_seq.as<uint8_t>() + ctx->fa_bases; a.seq_off_base = ctx->fa_bases;
         a.rec_pos = ctx->b_fa_rec_pos.as<int64_t>(); a.seq_off = ctx->b_seq_off.as<int64_t>() + ctx->fa_n; a.rec_cap = want_cap;
         a.st_carry = ctx->b_fa_status.as<uint64_t>(); a.st_keep = a.st_carry + tiles; a.st_rec = a.st_keep + tiles;
         a.ticket = &M->ticket; a.flags = &M->fa_flags; a.totals = M->fa_totals;
+        a.fastq = ctx->fa_fastq; a.line_base = ctx->fa_lines; a.text_gbase = ctx->fa_text_bytes; a.st_nl = a.st_rec + tiles;
+        a.rec_gpos = ctx->b_fa_rec_gpos.as<int64_t>(); a.qual_gpos = ctx->b_fa_qual_gpos.as<int64_t>(); a.rec_gcap = ctx->fa_gcap;
         CK(launch_fasta_tokenize(a, ctx->st));
         ctx->launches++;
-        struct { int flags, pad; long long tot[2]; } h;
+        struct { int flags, pad; long long tot[3]; } h;
         CK(cudaMemcpyAsync(&h, &M->fa_flags, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
-        if (h.flags) FAIL(RAFTGPU_E_UNSUPPORTED, "FASTA text needs the host reader (FASTQ '+' line, CR LF line ends, or no leading '>' / '@')");
+        if (h.flags) FAIL(RAFTGPU_E_UNSUPPORTED, "read text needs the host reader (FASTQ that is not strictly four lines per record, a '+' line in FASTA, CR LF line ends, or no leading '>' / '@')");
         if (h.tot[0] > want_cap) { want_cap = h.tot[0]; continue; } // more records than the optimistic capacity: redo this chunk
         const int64_t nrec = h.tot[0];
         // names of this chunk's records
@@ -552,6 +564,7 @@ static int fasta_chunk(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len, bool
         CKL();
         CK(cudaStreamSynchronize(ctx->st));
         ctx->fa_n += nrec; ctx->fa_bases += h.tot[1]; ctx->fa_name_bytes += nb;
+        ctx->fa_lines += h.tot[2]; ctx->fa_text_bytes += len;
         return RAFTGPU_OK;
     }
     FAIL(RAFTGPU_E_STATE, "FASTA record capacity retry failed");
@@ -562,10 +575,10 @@ extern "C" int raftgpu_ingest_fasta(raftgpu_ctx* ctx, const uint8_t* text, size_
     if (!ctx || (!text && nbytes)) return RAFTGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
     int st;
-    const bool first = !ctx->fasta_active;
-    if (first) {
+    const bool begin = !ctx->fasta_active;
+    if (begin) {
         if ((st = raftgpu_reset(ctx))) return st;
-        ctx->fasta_active = true; ctx->fa_rec_cap = 0;
+        ctx->fasta_active = true; ctx->fa_rec_cap = 0; ctx->fa_gcap = 0;
         cudaEventRecord(ctx->ev[0], ctx->st);
         if (total_hint) CK(ctx->b_seq.ensure((size_t)total_hint + 64));
     }
@@ -582,6 +595,24 @@ extern "C" int raftgpu_ingest_fasta(raftgpu_ctx* ctx, const uint8_t* text, size_
         CK(cudaStreamSynchronize(ctx->st));
         dtext = d;
     }
+    const bool first = ctx->fa_text_bytes == 0; // nothing tokenised yet
+    if (!ctx->fa_mode_known && total) { // strict FASTQ?  '@' first and a '+' opening the third line (anything less regular fails the checks later)
+        const size_t         peek = std::min<size_t>(total, 64u << 10);
+        std::vector<uint8_t> head(peek);
+        CK(cudaMemcpy(head.data(), dtext, peek, cudaMemcpyDeviceToHost));
+        size_t p = 0;
+        int    nl = 0;
+        while (p < peek && nl < 2) { if (head[p] == '\n') nl++; p++; }
+        const bool decided = head[0] != '@' || (nl == 2 && p < peek) || peek < total; // not FASTQ, or three lines seen, or lines too long to bother
+        if (!decided && !last_chunk) { // too little text to tell: keep it for the next call
+            std::vector<uint8_t> all(total);
+            CK(cudaMemcpy(all.data(), dtext, total, cudaMemcpyDeviceToHost));
+            ctx->fa_carry.swap(all);
+            return RAFTGPU_OK;
+        }
+        ctx->fa_fastq = head[0] == '@' && nl == 2 && p < peek && head[p] == '+';
+        ctx->fa_mode_known = true;
+    }
     size_t proc = total;
     if (!last_chunk && total) { // hold back the unterminated last line
         size_t scan = std::min<size_t>(total, 1 << 20);
@@ -597,6 +628,11 @@ extern "C" int raftgpu_ingest_fasta(raftgpu_ctx* ctx, const uint8_t* text, size_
         proc = (size_t)(nlpos + 1);
         ctx->fa_carry.assign(tail.begin() + (proc - (total - scan)), tail.end());
     } else ctx->fa_carry.clear();
+    if (proc) { // does the text seen so far end with a newline?  (only the last chunk can end without one)
+        uint8_t b = '\n';
+        if (last_chunk) CK(cudaMemcpy(&b, dtext + proc - 1, 1, cudaMemcpyDeviceToHost));
+        ctx->fa_ends_nl = b == '\n';
+    }
     st = fasta_chunk(ctx, dtext, (int64_t)proc, first, last_chunk != 0);
     if (st) { raftgpu_reset(ctx); return st; }
     if (!last_chunk) return RAFTGPU_OK;
@@ -608,6 +644,23 @@ extern "C" int raftgpu_ingest_fasta(raftgpu_ctx* ctx, const uint8_t* text, size_
     }
     CK(cudaMemcpy(ctx->b_seq_off.as<int64_t>() + n, &ctx->fa_bases, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->b_name_off.as<int64_t>() + n, &ctx->fa_name_bytes, 8, cudaMemcpyHostToDevice));
+    if (ctx->fa_fastq) { // four lines per record, and every quality line as long as its bases (kseq.h:290-296)
+        const int64_t lines = ctx->fa_lines + (ctx->fa_ends_nl ? 0 : 1);
+        int           bad = lines != 4 * n;
+        if (!bad && n > 0) {
+            Misc* M = ctx->misc();
+            CK(cudaMemsetAsync(&M->fa_flags, 0, sizeof(int), ctx->st));
+            launch_fastq_verify(n, ctx->b_seq_off.as<int64_t>(), ctx->b_fa_rec_gpos.as<int64_t>(), ctx->b_fa_qual_gpos.as<int64_t>(),
+                                ctx->fa_text_bytes + (ctx->fa_ends_nl ? 0 : 1), &M->fa_flags, ctx->st);
+            CKL();
+            CK(cudaMemcpyAsync(&bad, &M->fa_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+        }
+        if (bad) {
+            raftgpu_reset(ctx);
+            FAIL(RAFTGPU_E_UNSUPPORTED, "FASTQ text is not strictly four lines per record with quality lines as long as the bases: use the host reader");
+        }
+    }
     CK(cudaMemsetAsync(ctx->b_seq.as<uint8_t>() + ctx->fa_bases, 0, 32, ctx->st));
     ctx->fasta_active = false;
     ctx->n = n; ctx->m = n; ctx->own_first = 0;

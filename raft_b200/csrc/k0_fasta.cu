@@ -16,9 +16,15 @@
 // Outputs: the arena, and per record its file position and its offset in the arena.  Names are cut out by two
 // tiny per-record kernels afterwards.
 //
-// Inputs this kernel does not take (the caller falls back to the host reader, raftgpu_load_fasta): FASTQ
-// ('+' at a line start), any '\r' before a newline (kseq's strip rule depends on the accumulated length,
-// kseq.h:189-190), a file that does not begin with '>' or '@', a marker as the very last byte.
+// FASTQ (template parameter FQ) is taken in its strict four-line form: '@' header, one line of bases, '+' line, one
+// line of qualities of the same length.  There the role of a line is its index in the file modulo 4, so the header
+// carry is replaced by a third look-back (newlines before the tile) and the kept bytes are the role-1 lines; the
+// length condition is checked per record afterwards (k_fastq_verify).
+//
+// Inputs this kernel does not take (the caller falls back to the host reader, raftgpu_load_fasta): FASTA with a '+'
+// at a line start, FASTQ with wrapped or truncated sequence / quality lines, any '\r' before a newline (kseq's
+// strip rule depends on the accumulated length, kseq.h:189-190), a file that does not begin with '>' or '@', a
+// marker as the very last byte.
 #include "kernels.h"
 
 namespace raftk {
@@ -83,6 +89,7 @@ __device__ __forceinline__ int f0_resolve_carry(const uint64_t* status, int tile
     return 0;
 }
 
+template <bool FQ>
 __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a)
 {
     extern __shared__ __align__(16) uint8_t f0_raw[];
@@ -120,8 +127,28 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
     if (lane == 0 && my_last >= 0) atomicMax(&s.last_nl, my_last);
     __syncthreads();
 
-    // ---- line starts in my two words: markers open header lines; '+' or a CR before a newline are not handled here
     const int wlo = tid * 2;
+    // ---- strict FASTQ: the role of a line is its index in the file modulo 4, so count the newlines before every line start
+    int64_t L0 = 0;      // index of the line that holds the tile's first byte
+    int     nl_before = 0; // newlines of the tile before my first word
+    if (FQ) {
+        int cnt[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int      lo = (wlo + i) << 5;
+            const unsigned valid = lo + 32 <= want ? 0xFFFFFFFFu : (lo < want ? ((1u << (want - lo)) - 1u) : 0u); // bytes past the file end were filled with newlines
+            cnt[i] = __popc(s.nl[wlo + i] & valid);
+        }
+        int tot_nl;
+        nl_before = block_exclusive_sum<int, F0_THREADS>(cnt[0] + cnt[1], s.scan_ws, &tot_nl);
+        if (tid == 0) lookback_publish(a.st_nl, tile, (uint64_t)tot_nl);
+        const int64_t base_nl = (int64_t)lookback_wait(a.st_nl, tile, (uint64_t)tot_nl, &s.bcast[0]);
+        if (tid == 0 && tile == a.n_tiles - 1) a.totals[2] = base_nl + tot_nl;
+        L0 = a.line_base + base_nl;
+        __syncthreads(); // scan_ws and bcast are reused below
+    }
+
+    // ---- line starts in my two words: markers open header lines; '+' or a CR before a newline are not handled here
     unsigned  mk[2] = {0, 0};
     int       flags = 0;
 #pragma unroll
@@ -143,9 +170,28 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
             int p = (w << 5) + bit;
             if (p >= want) break;
             uint8_t c = s.text[p];
-            if (c == '>' || c == '@') {
-                mk[i] |= 1u << bit;
-                if (t0 + p == a.nbytes - 1) flags |= 8; // marker as the last byte of the file: kseq returns no record
+            bool    drop_line; // the whole line is left out of the arena
+            if (FQ) {
+                const int64_t ln = L0 + nl_before + (i ? __popc(s.nl[wlo]) : 0) + __popc(nlw & ((1u << bit) - 1u)); // bytes < want here: the fill is never counted
+                const int     role = (int)(ln & 3);
+                if (role == 0) {
+                    if (c != '@') flags |= 16;
+                    mk[i] |= 1u << bit;
+                    if ((ln >> 2) < a.rec_gcap) a.rec_gpos[ln >> 2] = a.text_gbase + t0 + p;
+                } else if (role == 1) {
+                    if (c == '>' || c == '+' || c == '@') flags |= 16; // kseq would end the sequence here (kseq.h:263)
+                } else if (role == 2) {
+                    if (c != '+') flags |= 16;
+                } else if ((ln >> 2) < a.rec_gcap) a.qual_gpos[ln >> 2] = a.text_gbase + t0 + p;
+                drop_line = role != 1;
+            } else {
+                drop_line = c == '>' || c == '@';
+                if (drop_line) {
+                    mk[i] |= 1u << bit;
+                    if (t0 + p == a.nbytes - 1) flags |= 8; // marker as the last byte of the file: kseq returns no record
+                } else if (c == '+') flags |= 2;
+            }
+            if (drop_line) {
                 // header line [p, e]: e = its newline (or the end of the tile)
                 int e = f0_next_bit(s.nl, p);
                 if (e >= F0_TILE) e = F0_TILE - 1;
@@ -155,15 +201,18 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
                     unsigned hi = ww == w1 ? (0xFFFFFFFFu >> (31 - (e & 31))) : 0xFFFFFFFFu;
                     atomicOr(&s.hdr[ww], lo & hi);
                 }
-            } else if (c == '+') flags |= 2;
+            }
         }
     }
-    if (t0 == 0 && tid == 0 && a.first_chunk && !(s.text[0] == '>' || s.text[0] == '@')) flags |= 4;
+    if (!FQ && t0 == 0 && tid == 0 && a.first_chunk && !(s.text[0] == '>' || s.text[0] == '@')) flags |= 4;
     if (tid == 0 && a.last_chunk && t0 + want == a.nbytes && s.text[want - 1] == '\r') flags |= 1; // CR at EOF: kseq's strip rule again
     if (flags) atomicOr(a.flags, flags);
 
-    // ---- carry: is the tile's first byte inside a header line?  (last-writer scan over tiles)
-    if (tid == 0) {
+    // ---- carry: is the tile's first byte inside a header line?  (last-writer scan over tiles; in FASTQ mode the role of
+    // the line that continues into the tile says it)
+    if (FQ) {
+        if (tid == 0) s.carry_in = !prev_nl && (L0 & 3) != 1;
+    } else if (tid == 0) {
         const int ql = s.last_nl;
         uint64_t  st;
         if (ql >= 0) { // the line open at the end of the tile starts at ql+1 (in this tile, or exactly at the next tile)
@@ -174,7 +223,7 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
         } else st = F0_TRANSPARENT;
         st_relaxed_u64(a.st_carry + tile, st);
     }
-    if (tid < 32) {
+    if (!FQ && tid < 32) {
         int cin = prev_nl ? 0 : f0_resolve_carry(a.st_carry, tile);
         if (lane == 0) {
             s.carry_in = cin;
@@ -303,10 +352,32 @@ int         fasta_tokenize_tiles(int64_t nbytes) { return (int)((nbytes + F0_TIL
 cudaError_t launch_fasta_tokenize(const FastaTokArgs& a, cudaStream_t st)
 {
     if (a.n_tiles <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_fasta_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(F0Smem));
-    if (e != cudaSuccess) return e;
-    k_fasta_tokenize<<<a.n_tiles, F0_THREADS, sizeof(F0Smem), st>>>(a);
-    return cudaGetLastError();
+    auto go = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(F0Smem));
+        if (e != cudaSuccess) return e;
+        kern<<<a.n_tiles, F0_THREADS, sizeof(F0Smem), st>>>(a);
+        return cudaGetLastError();
+    };
+    return a.fastq ? go(k_fasta_tokenize<true>) : go(k_fasta_tokenize<false>);
+}
+
+// ---------------------------------------------------------------- strict FASTQ: quality lines
+// kseq reads quality lines until it has as many bytes as bases (kseq.h:290-296).  With exactly one quality line of the
+// same length, which ends right before the next record's '@' (or the end of the file), the four-lines-per-record reading
+// of k_fasta_tokenize<true> is what kseq does; anything else (wrapped or truncated qualities) is left to the host reader.
+__global__ void __launch_bounds__(256) k_fastq_verify(int64_t n, const int64_t* __restrict__ seq_off, const int64_t* __restrict__ rec_gpos,
+                                                      const int64_t* __restrict__ qual_gpos, int64_t file_end, int* flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t bases = seq_off[i + 1] - seq_off[i];
+    const int64_t next = i + 1 < n ? rec_gpos[i + 1] : file_end; // one past the quality line's newline (a missing final newline is counted by the caller)
+    if (next - qual_gpos[i] - 1 != bases) atomicOr(flags, 16);
+}
+void launch_fastq_verify(int64_t n, const int64_t* seq_off, const int64_t* rec_gpos, const int64_t* qual_gpos, int64_t file_end, int* flags,
+                         cudaStream_t st)
+{
+    if (n > 0) k_fastq_verify<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seq_off, rec_gpos, qual_gpos, file_end, flags);
 }
 
 // ---------------------------------------------------------------- names: header up to the first isspace byte (kseq.h:254)

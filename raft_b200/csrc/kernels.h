@@ -33,9 +33,20 @@ struct FastaTokArgs {
     int64_t        rec_cap;
     uint64_t *     st_carry, *st_keep, *st_rec; // n_tiles words each, zeroed
     int*           ticket;    // zeroed
-    int*           flags;     // 1 CR before newline, 2 '+' line (FASTQ), 4 no leading marker, 8 marker is the last byte
-    long long*     totals;    // [0] records, [1] kept bytes of this chunk
+    int*           flags;     // 1 CR before newline, 2 '+' line (FASTQ), 4 no leading marker, 8 marker is the last byte,
+                              // 16 not a strict four-line FASTQ (fastq mode)
+    long long*     totals;    // [0] records, [1] kept bytes, [2] newlines (fastq mode) of this chunk
+    // strict four-line FASTQ mode: line k of the file has role k & 3 (0 '@' header, 1 bases, 2 '+' line, 3 qualities)
+    int            fastq;
+    int64_t        line_base;  // lines before this chunk
+    int64_t        text_gbase; // file offset of the chunk's first byte
+    uint64_t*      st_nl;      // n_tiles words, zeroed
+    int64_t *      rec_gpos, *qual_gpos; // per record of the FILE (index = line / 4): file offsets of its '@' and of its quality line
+    int64_t        rec_gcap;
 };
+// strict FASTQ: every record's quality line is as long as its bases and ends right before the next record (or the file)
+void launch_fastq_verify(int64_t n, const int64_t* seq_off, const int64_t* rec_gpos, const int64_t* qual_gpos, int64_t file_end, int* flags,
+                         cudaStream_t st);
 int         fasta_tokenize_tiles(int64_t nbytes);
 cudaError_t launch_fasta_tokenize(const FastaTokArgs& a, cudaStream_t st);
 void launch_fasta_name_len(const uint8_t* text, int64_t nbytes, const int64_t* rec_pos, int64_t n, int32_t* name_len, cudaStream_t st);

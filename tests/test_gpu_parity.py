@@ -453,11 +453,64 @@ def test_device_fasta_ingest_matches_kseq_grammar(name):
 
 def test_device_fasta_ingest_rejects_what_it_does_not_take():
     p = api.AlgoParams(est_cov=3)
-    for text in (b"@a\nACGT\n+\nIIII\n", b">a\r\nACGT\r\n", b"junk\n>a\nAC\n", b">a\nAC\n>"):
+    for text in (b">a\r\nACGT\r\n", b"junk\n>a\nAC\n", b">a\nAC\n>", b">a\nAC\n+\nII\n",
+                 b"@a\nACGT\nAC\n+\nIIII\nII\n",            # FASTQ with wrapped bases / qualities
+                 b"@a\nACGT\n+\nIII\n@b\nAC\n+\nII\n",      # quality line shorter than the bases (kseq would read on)
+                 b"@a\nACGT\n+\nIIIII\n",                    # longer
+                 b"@a\nACGT\n+\nIIII\n@b\nAC\n+\n",          # truncated last record
+                 b"@a\r\nACGT\r\n+\r\nIIII\r\n"):
         ctx = api.Context(p)
         with pytest.raises(api.RaftError) as ei:
             ctx.ingest_fasta(np.frombuffer(text, np.uint8), len(text), last=True)
-        assert ei.value.status == -12
+        assert ei.value.status == -12, text
+        ctx.close()
+
+
+def _fastq_variants():
+    rng = np.random.default_rng(11)
+    lens = (1, 59, 0, 16384, 16383, 40000, 7, 100000, 3, 0, 250, 33000)
+    seqs = [bytes(rng.choice(list(b"ACGTN"), int(L)).astype(np.uint8)) for L in lens]
+    names = [b"q%d" % i for i in range(len(seqs))]
+    def build(comment=b"", plus_name=False, trailing=True, at_quals=False):
+        out = []
+        for i, (nm, sq) in enumerate(zip(names, seqs)):
+            q = bytes(rng.integers(33, 74, len(sq)).astype(np.uint8))
+            if at_quals and q:
+                q = (b"@" if i % 2 else b"+") + q[1:]   # a quality line may start with '@' or '+': only its position says what it is
+            out.append(b"@" + nm + ((b" " + comment) if comment else b"") + b"\n" + sq + b"\n+" + (nm if plus_name else b"") + b"\n" + q + b"\n")
+        txt = b"".join(out)
+        return txt if trailing else txt[:-1]
+    return {"plain": build(), "comment_plusname": build(b"a comment\tx", True), "noeol": build(trailing=False), "at_in_quals": build(at_quals=True),
+            "huge_header": build(b"c" * 20000)}
+
+
+@pytest.mark.parametrize("name", sorted(_fastq_variants()))
+def test_device_fastq_ingest_matches_kseq_grammar(name):
+    """Row f2: strict four-line FASTQ is tokenised on the device (line role = line index mod 4) and yields kseq's records."""
+    text = _fastq_variants()[name]
+    ref = O.parse_fasta(text)
+    assert ref.n == 12
+    p = api.AlgoParams(est_cov=3)
+    paf = b"".join(b"\t".join([b"q3", b"16384", b"0", b"61", b"+", b"q%d" % j, b"1", b"0", b"1", b"1", b"1", b"9"]) + b"\n" for j in (5, 7))
+    want = O.run(ref, paf, O.make_params(est_cov=3))
+    assert want.status == 0
+    for chunks in (None, [5, 1000, 16384, 1, 70000, len(text)]):
+        ctx = api.Context(p)
+        buf = np.frombuffer(text, np.uint8)
+        if chunks is None:
+            ctx.ingest_fasta(buf, len(text), last=True, total_hint=len(text))
+        else:
+            pos = 0
+            for k, c in enumerate(chunks):
+                piece = buf[pos:pos + c]
+                ctx.ingest_fasta(np.ascontiguousarray(piece), len(piece), last=(k == len(chunks) - 1))
+                pos += len(piece)
+        ctx.ingest_paf(np.frombuffer(paf, np.uint8), len(paf), last=True)
+        st = ctx.run()
+        assert st.n_reads == ref.n
+        np.testing.assert_array_equal(ctx.table(api.TAB_BIN_OFF), want.bin_off)
+        assert ctx.fetch(api.OUT_READS_FASTA) == want.fasta     # names, lengths and every base in place
+        assert ctx.fetch(api.OUT_COVERAGE) == want.cov_txt
         ctx.close()
 
 
