@@ -519,9 +519,12 @@ static int fasta_chunk(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len, bool
             ctx->fa_rec_cap = cap;
         }
         if (ctx->fa_fastq && need + 2 > ctx->fa_gcap) { // file offsets of every record's '@' and quality line (index = line / 4)
-            const int64_t cap = need + need / 4 + 2, keep = sizeof(int64_t) * (size_t)std::min<int64_t>(ctx->fa_gcap, ctx->fa_n + 2);
-            CK(ctx->b_fa_rec_gpos.ensure(sizeof(int64_t) * (size_t)cap, (size_t)keep, ctx->st));
-            CK(ctx->b_fa_qual_gpos.ensure(sizeof(int64_t) * (size_t)cap, (size_t)keep, ctx->st));
+            // entries written so far: a record's '@' offset once its line 4k was seen, its quality offset once line 4k+3 was
+            const int64_t cap = need + need / 4 + 2;
+            const size_t  keep_rec = sizeof(int64_t) * (size_t)std::min<int64_t>(ctx->fa_gcap, (ctx->fa_lines + 3) >> 2);
+            const size_t  keep_qual = sizeof(int64_t) * (size_t)std::min<int64_t>(ctx->fa_gcap, ctx->fa_lines >> 2);
+            CK(ctx->b_fa_rec_gpos.ensure(sizeof(int64_t) * (size_t)cap, keep_rec, ctx->st));
+            CK(ctx->b_fa_qual_gpos.ensure(sizeof(int64_t) * (size_t)cap, keep_qual, ctx->st));
             ctx->fa_gcap = cap;
         }
         CK(ctx->b_fa_rec_pos.ensure(sizeof(int64_t) * (size_t)(want_cap + 1)));
