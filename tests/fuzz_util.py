@@ -69,3 +69,30 @@ def fuzz_case(seed):
     paf = eol.join(lines) + (eol if lines and rng.integers(0, 4) else b"")
     args = ["-r", str(r), "-e", str(e_cov), "-m", repr(mul), "-l", str(l), "-p", str(p), "-f", str(f), "-v", str(v)]
     return fa, paf, args
+
+
+def fuzz_fastq_text(seed):
+    """Random FASTQ / mixed FASTA+FASTQ text inside kseq's grammar (kseq.h:240-298): wrapped bases and qualities,
+    '+name' lines, quality lines that start with '@' or '+', empty records, missing final newline."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 9))
+    out, lens = [], []
+    for i in range(n):
+        L = int(rng.choice([0, 1, 5, 60, 61, 200, int(rng.integers(1, 500))]))
+        seq = bytes(rng.choice(list(b"ACGTN"), L).astype(np.uint8))
+        name = b"fq%d_%d" % (seed, i)
+        wrap = int(rng.choice([0, 0, 7, 60]))
+        lines = lambda b: b"\n".join(b[k:k + wrap] for k in range(0, len(b), wrap)) if (wrap and b) else b
+        if rng.integers(0, 4) == 0:                     # a FASTA record in between
+            out.append(b">" + name + b" c\n" + lines(seq) + b"\n")
+        else:
+            q = bytes(rng.integers(33, 74, L).astype(np.uint8))
+            if L and rng.integers(0, 3) == 0:
+                q = (b"@" if rng.integers(0, 2) else b"+") + q[1:]
+            out.append(b"@" + name + (b" comment" if rng.integers(0, 2) else b"") + b"\n" + lines(seq) + b"\n+" +
+                       (name if rng.integers(0, 2) else b"") + b"\n" + lines(q) + b"\n")
+        lens.append(L)
+    text = b"".join(out)
+    if rng.integers(0, 3) == 0:
+        text = text[:-1]
+    return text, lens

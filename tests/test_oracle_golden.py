@@ -7,7 +7,7 @@ import pytest
 from golden_util import SUFS, args_to_kw, check_output, load_inputs, manifest, stdout_value
 from oracle import oracle as O
 from raft_b200 import synth
-from fuzz_util import fuzz_case
+from fuzz_util import fuzz_case, fuzz_fastq_text
 from sim_util import sim_dataset
 
 CASES = manifest()
@@ -127,3 +127,44 @@ def test_oracle_fuzz_matches_reference_binary(block):
             assert files.get(suf, b"") == data, (seed, suf, args)
         compared += 1
     assert compared >= 10
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/raft not built (reference sources not mounted)")
+def test_oracle_fastq_grammar_fuzz_matches_reference_binary():
+    """kseq's FASTQ reading (qualities read by length, wrapped lines, '@' / '+' opening a quality line, FASTA records in
+    between): the oracle's parser and the reference binary see the same reads -- reads.fasta and coverage.txt of a run
+    without overlaps list every read's name, length and bases."""
+    for seed in range(60):
+        text, lens = fuzz_fastq_text(seed)
+        reads = O.parse_fasta(text)
+        paf = b"x\n"                                   # no record: the reference refuses an empty PAF file
+        res = O.run(reads, paf, O.make_params(est_cov=2, reso=10))
+        assert res.status == 0
+        with tempfile.TemporaryDirectory() as d:
+            fp, pp = os.path.join(d, "r.fq"), os.path.join(d, "o.paf")
+            open(fp, "wb").write(text)
+            open(pp, "wb").write(paf)
+            rc, out, files = O.run_ref(fp, pp, d, ["-e", "2", "-r", "10"])
+        assert rc == 0, (seed, out)
+        assert files.get("reads.fasta", b"") == res.fasta, seed
+        assert files.get("coverage.txt", b"") == res.cov_txt, seed
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/raft not built (reference sources not mounted)")
+@pytest.mark.parametrize("text", [b"@a\nACGT\n+\nIIII\n@b\nACGT\n+\nII\n",          # truncated quality at the end of the file: record dropped
+                                  b"@a\nACGT\n+\nIIIII\n@b\nAC\n+\nII\n",          # quality longer than the bases: kseq stops there (kseq.h:296)
+                                  b"@a\nACGT\n+\nIII\n@b\nAC\n+\nII\n",            # shorter: the next lines are read as quality
+                                  b"@a\nAC\nGT\n+\nII\nII\n>b\nACG\n",             # wrapped FASTQ, then FASTA
+                                  b"@a\n\n+\n\n@b\nA\n+\nI"])                      # empty record, no final newline
+def test_oracle_fastq_error_cases_match_reference_binary(text):
+    reads = O.parse_fasta(text)
+    res = O.run(reads, b"x\n", O.make_params(est_cov=2, reso=10))
+    assert res.status == 0
+    with tempfile.TemporaryDirectory() as d:
+        fp, pp = os.path.join(d, "r.fq"), os.path.join(d, "o.paf")
+        open(fp, "wb").write(text)
+        open(pp, "wb").write(b"x\n")
+        rc, out, files = O.run_ref(fp, pp, d, ["-e", "2", "-r", "10"])
+    assert rc == 0, out
+    assert files.get("reads.fasta", b"") == res.fasta
+    assert files.get("coverage.txt", b"") == res.cov_txt
