@@ -48,6 +48,14 @@ class OrcResult(C.Structure):
                 ("fasta", _P8), ("fasta_len", C.c_int64)]
 
 
+class OrcDigestResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("bad_index", C.c_int64), ("n_rec", C.c_int64),
+                ("symmetric", C.c_int32), ("high_cov", C.c_int32), ("real_reads", C.c_int32),
+                ("n_frag", C.c_int64), ("n_rep", C.c_int64), ("total_cov", C.c_int64), ("total_windows", C.c_int32),
+                ("total_repeat_len", C.c_int64), ("total_read_len", C.c_int64),
+                ("digest", C.c_uint64 * 4), ("bytes", C.c_int64 * 4)]
+
+
 class OrcFasta(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("seq_off", _P64), ("seq", _P8), ("name_off", _P64), ("names", _P8)]
 
@@ -65,6 +73,9 @@ def lib():
         _lib.orc_run.argtypes = [C.POINTER(OrcReads), C.c_void_p, C.c_int64, C.POINTER(OrcParams), C.c_int,
                                  C.POINTER(OrcResult)]
         _lib.orc_free.argtypes = [C.POINTER(OrcResult)]
+        _lib.orc_run_digest.restype = C.c_int
+        _lib.orc_run_digest.argtypes = [C.POINTER(OrcReads), C.c_void_p, C.c_int64, C.POINTER(OrcParams), C.c_int,
+                                        C.POINTER(OrcDigestResult)]
         _lib.orc_parse_fasta.restype = C.c_int64
         _lib.orc_parse_fasta.argtypes = [C.c_void_p, C.c_int64, C.POINTER(OrcFasta)]
         _lib.orc_free_fasta.argtypes = [C.POINTER(OrcFasta)]
@@ -140,6 +151,24 @@ def run(reads, paf: bytes, params: OrcParams, text=True):
             out.fasta = _bytes(res.fasta, res.fasta_len)
     L.orc_free(C.byref(res))
     return out
+
+
+def run_digest(reads, paf, params: OrcParams, threads=None):
+    """orc_run_digest: the whole path with `threads` host threads, outputs reported as (bytes, digest) per file.
+    `paf` may be bytes or a uint8 numpy array; nothing is copied.  Returns the OrcDigestResult structure
+    (digest[k] / bytes[k] indexed coverage.txt, long_repeats.txt, long_repeats.bed, reads.fasta)."""
+    L = lib()
+    seq_off = np.ascontiguousarray(reads.seq_off, dtype=np.int64)
+    name_off = np.ascontiguousarray(reads.name_off, dtype=np.int64)
+    seq = np.ascontiguousarray(reads.seq, dtype=np.uint8)
+    names = np.ascontiguousarray(reads.names, dtype=np.uint8)
+    rd = OrcReads(len(seq_off) - 1, seq_off.ctypes.data, seq.ctypes.data if seq.size else None,
+                  name_off.ctypes.data, names.ctypes.data if names.size else None)
+    pafb = np.frombuffer(paf, dtype=np.uint8) if isinstance(paf, (bytes, bytearray)) else np.ascontiguousarray(paf, dtype=np.uint8)
+    res = OrcDigestResult()
+    L.orc_run_digest(C.byref(rd), pafb.ctypes.data if pafb.size else None, pafb.size, C.byref(params),
+                     int(threads or os.cpu_count() or 1), C.byref(res))
+    return res
 
 
 class Reads:

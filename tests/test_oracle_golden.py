@@ -31,6 +31,52 @@ def test_oracle_matches_reference_golden(entry):
         res.total_repeat_len / res.total_read_len)
 
 
+def _assert_digest_mode_equals_run(reads, paf, prm, threads):
+    """orc_run_digest (the multi-threaded form used for outputs too large to hold) reports exactly the digests, lengths
+    and counters of the bytes orc_run materialises."""
+    res = O.run(reads, paf, prm)
+    dg = O.run_digest(reads, paf, prm, threads=threads)
+    assert dg.status == res.status
+    if res.status:
+        assert dg.bad_index == res.bad_index
+        return
+    for k, data in enumerate((res.cov_txt, res.rep_txt, res.bed_txt, res.fasta)):
+        assert dg.bytes[k] == len(data), k
+        assert dg.digest[k] == O.digest(data), k
+    assert (dg.n_rec, dg.symmetric, dg.high_cov, dg.real_reads, dg.n_frag) == (res.n_rec, res.symmetric, res.high_cov, res.real_reads, res.n_frag)
+    assert (dg.total_cov, dg.total_windows, dg.total_repeat_len, dg.total_read_len) == (res.total_cov, res.total_windows,
+                                                                                        res.total_repeat_len, res.total_read_len)
+    assert dg.n_rep == len(res.rep_s)
+
+
+@pytest.mark.parametrize("entry", CASES, ids=[e["name"] for e in CASES])
+def test_digest_mode_matches_run_on_golden(entry):
+    fa, paf = load_inputs(entry)
+    for threads in (1, 3):
+        _assert_digest_mode_equals_run(O.parse_fasta(fa), paf, O.make_params(**args_to_kw(entry["args"])), threads)
+
+
+def test_digest_mode_matches_run_on_fuzz_and_errors():
+    for seed in range(150):
+        fa, paf, args = fuzz_case(seed)
+        _assert_digest_mode_equals_run(O.parse_fasta(fa), paf, O.make_params(**args_to_kw(args)), 1 + seed % 4)
+    reads, paf = sim_dataset(5)
+    _assert_digest_mode_equals_run(reads, paf, O.make_params(est_cov=30, repeat_length=4000, read_length=8000, flanking_length=300, overlap_length=200), 4)
+    rd = O.parse_fasta(b">a\nACGTACGTAC\n>b\nACGTACGTACGG\n")
+    line = lambda *f: b"\t".join(str(x).encode() for x in f) + b"\n"
+    ok = line("a", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255)
+    for bad in (line("zz", 10, 0, 10, "+", "b", 12, 0, 10, 10, 10, 255), line("a", 10, 0, 500, "+", "b", 12, 0, 10, 10, 10, 255)):
+        _assert_digest_mode_equals_run(rd, ok * 3 + bad + ok, O.make_params(est_cov=1), 2)
+    _assert_digest_mode_equals_run(rd, ok, O.make_params(est_cov=1, read_length=50, repeat_length=100), 2)
+    _assert_digest_mode_equals_run(O.parse_fasta(b">a\nAC\n>a\nGT\n"), b"", O.make_params(est_cov=1), 2)
+
+
+@pytest.mark.parametrize("cfg,scale,sym", [("C2", 0.0004, True), ("C5", 0.002, False), ("C4", 0.001, True)])
+def test_digest_mode_matches_run_on_config_shapes(cfg, scale, sym):
+    ds = synth.make_dataset(cfg, scale, sym, seed=77)
+    _assert_digest_mode_equals_run(ds.reads, ds.paf, O.make_params(**args_to_kw(ds.args)), 8)
+
+
 def test_oracle_defined_domain_errors():
     fa = b">a\nACGTACGTAC\n>b\nACGTACGTACGG\n"
     reads = O.parse_fasta(fa)
