@@ -20,7 +20,7 @@ $(OBJ)/host_io.o: $(SRC)/host_io.cpp include/raft_b200.h
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz -lnccl
 
 raft_b200/libraft_synth.so: $(SRC)/synth_gen.cu $(SRC)/common.cuh
 	$(NVCC) $(NVFLAGS) -shared $< -o $@

@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py — PAF overlaps/sec of the fragmentation hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S] [--config C2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C4|C5] [--asymmetric] [--scale S]
 
 A step = one pass of the whole path over one synthetic input set:
     reads resident -> name table + layout -> PAF tokenise -> coverage scatter + scan -> repeats + cut
     points -> coverage.txt / long_repeats.txt / reads.fasta bytes materialised (window by window).
-`value`  : inputs already in HBM, outputs materialised into HBM windows (device-resident).
-`e2e`    : same call sequence through the C ABI with pinned HOST inputs and HOST outputs (H2D + D2H inside).
-`--impl reference`: the unmodified reference binary (oracle/_ref/raft) on a bounded sample of the same
-workload, on the host cores (the program is single-threaded).
+`value`   : inputs already in HBM, outputs materialised into HBM windows (device-resident).
+`e2e`     : same call sequence through the C ABI with pinned HOST inputs and HOST outputs (H2D + D2H inside).
+`parity`  : the outputs of the benchmarked runs, proven: 64-bit digests of the three output files computed on the device
+            (not timed) against the CPU oracle on the SAME full-size inputs (oracle/orc_run_digest, all host cores), the
+            e2e run against the device-resident run, and the file -> file leg against the unmodified reference binary.
+`file_to_file` : raft_b200/raft and oracle/_ref/raft on the same files of a 1/16 sample (whole config for C1): both timers,
+            outputs compared byte by byte.  The reference's time on that sample is `cpu_baseline`.
+`--impl reference`: the unmodified reference binary (oracle/_ref/raft) on a bounded sample of the same workload, on the host
+cores (the program is single-threaded).
 One JSON line on stdout (rank 0).
 """
 import argparse
+import filecmp
 import json
 import os
 import shutil
@@ -29,10 +35,59 @@ sys.path.insert(0, ROOT)
 METRIC = "PAF overlaps/sec end-to-end fragmentation"
 UNIT = "overlaps/s"
 WINDOW = 1 << 30  # device output window (bytes)
+STREAMS = ("coverage.txt", "long_repeats.txt", "reads.fasta")
+
+CONFIG_DESC = {
+    "C1": "synthetic chr11-2M-shaped: 2 Mbp genome, 42x error-free reads, simulated all-vs-all PAF",
+    "C2": "synthetic human 32x ONT-Duplex-shaped reads + all-vs-all PAF (~3.1 Gbp genome, defaults -r 50 -l 20000)",
+    "C4": "ultralong-ONT non-uniform length distribution (N50 ~100 kb) with dense contained-read overlaps (500 Mbp genome, 30x)",
+    "C5": "repeat-heavy synthetic genome (segmental duplications), 200 Mbp 30x, overlaps capped at 2000 per read",
+}
+OVL_PER_UNIT = {"C2": 2.3e8, "C1": 4.5e5, "C4": 3e7, "C5": 5e7}       # overlaps at scale 1.0, for sample sizing
+SAMPLE_DIV = {"C1": 1, "C2": 16, "C4": 16, "C5": 16}                   # file -> file sample = config / this
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def config_block(a, args):
+    """Static description of the workload: identical in the default arm, the reference arm and at every N."""
+    sym = not a.asymmetric
+    return {"workload": f"{a.config}: {CONFIG_DESC[a.config]}; {'symmetric (both directions of every pair)' if sym else 'asymmetric (one record per pair, q < t)'} "
+                        f"PAF grouped by query; raft {' '.join(args)}; genome scale {a.scale:g}",
+            "config_id": a.config, "scale": a.scale, "symmetric": sym, "flags": " ".join(args),
+            "l2": "inputs and outputs are far larger than the 126 MB L2 (C1: every step re-reads 130 MB of inputs and rewrites its outputs); no explicit flush"}
+
+
+def digest_key(a):
+    return f"{a.config}:{a.scale:g}:{'asym' if a.asymmetric else 'sym'}"
+
+
+def load_expected(key):
+    """Digests of an earlier, oracle-verified N=1 run of the same inputs: this box's scratch copy first, then the committed table."""
+    for path in (os.path.join(tempfile.gettempdir(), "raft_b200_digests.json"), os.path.join(ROOT, "profiles", "expected_digests.json")):
+        try:
+            d = json.load(open(path)).get(key)
+            if d:
+                return d, os.path.relpath(path, ROOT) if path.startswith(ROOT) else path
+        except Exception:
+            pass
+    return None, None
+
+
+def save_digests(key, entry):
+    for path in (os.path.join(tempfile.gettempdir(), "raft_b200_digests.json"), os.path.join(ROOT, "gpurun_out", "digests.json")):
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            try:
+                cur = json.load(open(path))
+            except Exception:
+                cur = {}
+            cur[key] = entry
+            json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+        except Exception:
+            pass
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -73,93 +128,91 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- reference arm / cpu baseline
-def write_sample_files(d, ds_host_reads, paf_bytes):
+# ----------------------------------------------------------------------------------------------- files for the CPU legs
+def write_sample_files(d, reads, paf_bytes):
+    """reads.fa (one line per sequence) + ovl.paf from host arrays."""
     import numpy as np
-    r = ds_host_reads
     fa = os.path.join(d, "reads.fa")
     with open(fa, "wb") as fh:
-        for i in range(r.n):
-            fh.write(b">" + bytes(r.names[r.name_off[i]:r.name_off[i + 1]]) + b"\n")
-            fh.write(r.seq[r.seq_off[i]:r.seq_off[i + 1]].tobytes() + b"\n")
+        for i in range(reads.n):
+            fh.write(b">" + bytes(reads.names[reads.name_off[i]:reads.name_off[i + 1]]) + b"\n")
+            fh.write(reads.seq[reads.seq_off[i]:reads.seq_off[i + 1]].tobytes() + b"\n")
     pf = os.path.join(d, "ovl.paf")
     with open(pf, "wb") as fh:
         fh.write(paf_bytes if isinstance(paf_bytes, (bytes, bytearray)) else np.asarray(paf_bytes).tobytes())
     return fa, pf
 
 
-def make_sample(config, target_overlaps, full_scale_overlaps_per_unit):
-    """Bounded sample of the workload for the CPU legs: same generator, smaller genome."""
-    import torch
-    scale = target_overlaps / full_scale_overlaps_per_unit
-    if torch.cuda.is_available():
-        from raft_b200 import synth_gpu
-        ds = synth_gpu.make_dataset_gpu(config, scale)
-        reads = ds.to_host_reads()
-        paf = ds.paf.cpu().numpy().tobytes()
-        args, n_ovl = ds.args, ds.n_overlaps
-        del ds
-        torch.cuda.empty_cache()
-    else:
-        from raft_b200 import synth
-        ds = synth.make_dataset(config, scale)
-        reads, paf, args, n_ovl = ds.reads, ds.paf, ds.args, ds.n_overlaps
-    return reads, paf, args, n_ovl, scale
-
-
-def run_reference_once(ref_bin, fa, pf, args, d):
+def run_raft_binary(binary, fa, pf, args, prefix, env=None):
+    """One file -> file run; returns (own timer seconds, wall seconds, overlaps from the log line, stdout)."""
     t0 = time.perf_counter()
-    p = subprocess.run([ref_bin] + list(args) + ["-o", os.path.join(d, "ref"), fa, pf], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    p = subprocess.run([binary] + list(args) + ["-o", prefix, fa, pf], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     wall = time.perf_counter() - t0
     if p.returncode != 0:
-        raise RuntimeError("reference failed: " + p.stdout[-2000:])
+        raise RuntimeError(f"{binary} failed ({p.returncode}): " + p.stdout[-2000:])
     own, n = wall, None
     for line in p.stdout.splitlines():
+        if "[raft_b200 timing]" in line:
+            log(line)
         if "program completed after" in line:
             own = float(line.split("after")[1].split()[0])
         if "length of alignments" in line:
             n = int(line.split("alignments")[1].strip().rstrip("()"))
-    return own, wall, n
+    return own, wall, n, p.stdout
 
 
-OVL_PER_UNIT = {"C2": 2.3e8, "C1": 4.5e5, "C4": 3e7, "C5": 5e7}  # overlaps at scale 1.0 (SURVEY.md §8.C), for sample sizing
+def scratch_dir(need_bytes):
+    """tmpfs when it has room next to the host RAM the run still needs (file times then measure the programs, not the disk)."""
+    try:
+        import psutil
+        st = shutil.disk_usage("/dev/shm")
+        if st.free > need_bytes * 1.2 and psutil.virtual_memory().available > need_bytes * 1.2 + (24 << 30):
+            return tempfile.mkdtemp(prefix="raft_b200_", dir="/dev/shm"), "tmpfs (/dev/shm)"
+    except Exception:
+        pass
+    return tempfile.mkdtemp(prefix="raft_b200_"), "disk (" + tempfile.gettempdir() + ")"
 
 
+# ----------------------------------------------------------------------------------------------- reference arm
 def reference_arm(a):
     from oracle import oracle as O
+    from raft_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if not O.have_ref():
         subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")])
     kind = "reference" if O.have_ref() else "port"
-    # ~1.2 M overlaps per step: about 5 s of the single-threaded reference
-    reads, paf, args, n_ovl, scale = make_sample(a.config, 1.2e6, OVL_PER_UNIT[a.config])
-    d = tempfile.mkdtemp(prefix="raft_ref_")
+    # bounded sample: the whole --steps/--warmup run should end within a few minutes at ~0.5 M overlaps/s of the single-threaded
+    # reference, and never exceed the 1/16 sample of the file -> file leg
+    runs = max(1, a.warmup + a.steps)
+    target = min(OVL_PER_UNIT[a.config] * a.scale / SAMPLE_DIV[a.config], 0.5e6 * 240.0 / runs)
+    scale = min(a.scale, max(target / OVL_PER_UNIT[a.config], 1e-4))
+    ds = synth.make_dataset(a.config, scale, symmetric=not a.asymmetric)  # host generator (numpy): no GPU library on this arm
+    reads, paf, args, n_ovl = ds.reads, ds.paf, ds.args, ds.n_overlaps
+    d, fs = scratch_dir(int(reads.seq_off[-1]) * 2.2 + len(paf) * 1.6)
     try:
         fa, pf = write_sample_files(d, reads, paf)
-        times = []
+        times, owns = [], []
         for it in range(a.warmup + a.steps):
             if kind == "reference":
-                own, wall, n = run_reference_once(O.REF_BIN, fa, pf, args, d)
+                own, wall, n, _ = run_raft_binary(O.REF_BIN, fa, pf, args, os.path.join(d, "ref"))
             else:
                 t0 = time.perf_counter()
                 res = O.run(reads, paf, O.make_params(**_kw(args)))
                 own = wall = time.perf_counter() - t0
                 n = res.n_rec
             if it >= a.warmup:
-                times.append(wall)
+                times.append(wall); owns.append(own)
         sec = sum(times) / len(times)
         v = n_ovl / sec
         out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/u8",
-               "data": "synthetic",
-               "config": {"workload": f"{a.config} synthetic human 32x ONT-Duplex-shaped reads + symmetric all-vs-all PAF, genome scale {a.scale:g} "
-                                      f"(raft {' '.join(args)}, defaults -r 50 -l 20000): the workload of the default arm, timed on a bounded sample",
-                          "sample": f"the same generator at genome scale {scale:.4g}, file to file",
-                          "n_overlaps": n_ovl, "n_reads": reads.n, "bases": int(reads.seq_off[-1]), "flags": " ".join(args)},
+               "data": "synthetic", "config": config_block(a, args),
                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
-                                "sample": f"{n_ovl} overlaps / {int(reads.seq_off[-1])} bases, file to file, wall clock around the process"},
+                                "reference_own_timer_s": sum(owns) / len(owns), "gbp_per_s": int(reads.seq_off[-1]) / sec / 1e9, "fs": fs,
+                                "sample": f"{a.config}-shaped at genome scale {scale:.4g} (1/{a.scale / scale:.3g} of the workload: {n_ovl} overlaps, "
+                                          f"{int(reads.seq_off[-1])} bases), file to file, wall clock around the process; the reference is O(records + bases)"},
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(out), flush=True)
     finally:
@@ -171,20 +224,18 @@ def _kw(args):
     return {m[args[k]]: int(args[k + 1]) for k in range(0, len(args), 2)}
 
 
-def host_can_hold(nbytes, reserve=40 << 30):
+def host_available():
     try:
         import psutil
-        return psutil.virtual_memory().available > nbytes + reserve
+        return psutil.virtual_memory().available
     except Exception:
-        return nbytes < (64 << 30)
+        return 48 << 30
 
 
 # ----------------------------------------------------------------------------------------------- our arm
 def emit_all_device(ctx, api, win, win2):
     """materialise every output stream into device window buffers, window by window.  The text streams go to `win2`
-    and the sequence stream to `win` through the asynchronous API: they run on two CUDA streams of the library, so the
-    issue-bound text formatter overlaps the bandwidth-bound gather."""
-    total = 0
+    and the sequence stream to `win` through the asynchronous API: they run on two CUDA streams of the library."""
     sizes = {w: ctx.output_size(w) for w in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA)}
     for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS):
         for off in range(0, sizes[which], WINDOW):
@@ -194,6 +245,72 @@ def emit_all_device(ctx, api, win, win2):
         ctx.fetch_async(api.OUT_READS_FASTA, off, win, min(WINDOW, n - off))
     ctx.sync()
     return sum(sizes.values())
+
+
+def device_digests(ctx, api, base=(0, 0, 0)):
+    """[(bytes, digest)] of coverage.txt, long_repeats.txt, reads.fasta, computed on the device from the context's state."""
+    out = {}
+    for k, (w, name) in enumerate(((api.OUT_COVERAGE, STREAMS[0]), (api.OUT_LONG_REPEATS, STREAMS[1]), (api.OUT_READS_FASTA, STREAMS[2]))):
+        out[name] = [int(ctx.output_size(w)), int(ctx.digest(w, base[k]))]
+    return out
+
+
+def oracle_digests(reads, paf, args, threads):
+    """The CPU oracle on the same inputs (all host cores): {stream: [bytes, digest]}, seconds, result struct."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    r = O.run_digest(reads, paf, O.make_params(**_kw(args)), threads=threads)
+    dt = time.perf_counter() - t0
+    if r.status:
+        raise RuntimeError(f"oracle failed on the bench inputs: status {r.status} at {r.bad_index}")
+    return {STREAMS[0]: [int(r.bytes[0]), int(r.digest[0])], STREAMS[1]: [int(r.bytes[1]), int(r.digest[1])],
+            STREAMS[2]: [int(r.bytes[3]), int(r.digest[3])]}, dt, r
+
+
+def file_to_file_leg(a, local, log):
+    """raft_b200/raft and the unmodified reference binary on the same files (1/SAMPLE_DIV of the workload); outputs compared byte by byte."""
+    import torch
+    from oracle import oracle as O
+    from raft_b200 import synth_gpu
+    if not O.have_ref():
+        return None
+    scale = a.scale / SAMPLE_DIV[a.config]
+    ds = synth_gpu.make_dataset_gpu(a.config, scale, symmetric=not a.asymmetric, device=f"cuda:{local}", with_seq=False)
+    d, fs = scratch_dir(ds.bases * 3.3 + ds.paf.numel() * 2.0)
+    try:
+        fa, pf = os.path.join(d, "reads.fa"), os.path.join(d, "ovl.paf")
+        chunk = max(1, int(ds.n * (1 << 30) / max(ds.bases, 1)))
+        tbuf = None
+        with open(fa, "wb") as fh:  # ">" name "\n" bases "\n", generated on the device a GiB at a time
+            for r0 in range(0, ds.n, chunk):
+                r1 = min(ds.n, r0 + chunk)
+                tbuf, nb = synth_gpu.gen_fasta_text(ds, r0, r1, tbuf)
+                fh.write(memoryview(tbuf[:nb].cpu().numpy()))
+        with open(pf, "wb") as fh:
+            fh.write(memoryview(ds.paf.cpu().numpy()))
+        args, n_s, bases, n_reads = ds.args, ds.n_overlaps, ds.bases, ds.n
+        paf_bytes = int(ds.paf.numel())
+        del ds, tbuf
+        torch.cuda.empty_cache()
+        env = dict(os.environ, RAFT_B200_DEVICE=str(local))
+        exe = os.path.join(ROOT, "raft_b200", "raft")
+        run_raft_binary(exe, fa, pf, args, os.path.join(d, "gpu"), env)          # warm-up: page cache, CUDA module load
+        g_own, g_wall, g_n, _ = run_raft_binary(exe, fa, pf, args, os.path.join(d, "gpu"), env)
+        r_own, r_wall, r_n, _ = run_raft_binary(O.REF_BIN, fa, pf, args, os.path.join(d, "ref"))
+        same = {s: filecmp.cmp(os.path.join(d, "gpu." + s), os.path.join(d, "ref." + s), shallow=False)
+                for s in ("coverage.txt", "long_repeats.txt", "long_repeats.bed", "reads.fasta")}
+        out_bytes = {s: os.path.getsize(os.path.join(d, "ref." + s)) for s in same}
+        ident = all(same.values()) and g_n == r_n == n_s
+        return {"sample": f"{a.config}-shaped at genome scale {scale:.4g} (1/{SAMPLE_DIV[a.config]} of the workload): {n_s} overlaps, {n_reads} reads, "
+                          f"{bases} bases, {paf_bytes} PAF bytes; the same reads.fa + ovl.paf given to both programs",
+                "fs": fs, "n_overlaps": n_s, "identical": bool(ident), "files_identical": same, "out_bytes": out_bytes,
+                "ours": {"t_file_s": g_own, "wall_s": g_wall, "overlaps_per_s": n_s / g_own, "gbp_per_s": bases / g_own / 1e9,
+                         "binary": "raft_b200/raft (second of two runs)"},
+                "reference": {"t_file_s": r_own, "wall_s": r_wall, "overlaps_per_s": n_s / r_own, "gbp_per_s": bases / r_own / 1e9,
+                              "binary": "oracle/_ref/raft (unmodified, 1 core)"},
+                "speedup_t_file": r_own / g_own}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def ours(a):
@@ -209,15 +326,13 @@ def ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries the JSON line only
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from raft_b200 import sharded
         return sharded.bench(a, rank, world, local, log)
 
     t_gen = time.perf_counter()
-    ds = synth_gpu.make_dataset_gpu(a.config, a.scale, device=f"cuda:{local}")
+    ds = synth_gpu.make_dataset_gpu(a.config, a.scale, symmetric=not a.asymmetric, device=f"cuda:{local}")
     log(f"[bench] generated {ds.meta} in {time.perf_counter() - t_gen:.1f}s")
     p = api.AlgoParams.from_args(ds.args)
     ctx = api.Context(p, local)
@@ -255,10 +370,22 @@ def ours(a):
     stage = {k: v / a.steps for k, v in stage.items()}
     out_bytes = [int(x) for x in st.out_bytes]
     n_ovl = int(st.n_records)
+    stats_line = {"symmetric": int(st.symmetric), "high_cov": int(st.high_cov), "n_fragments": int(st.n_fragments), "n_repeats": int(st.n_repeats),
+                  "n_bins": int(st.n_bins)}
+
+    # ---- parity, part 1 (not timed): digests of the three output streams of the state the timed steps left behind
+    checks = []
+    dig_dev = device_digests(ctx, api)
+    key = digest_key(a)
+    exp, exp_src = load_expected(key)
+    if exp is not None:
+        checks.append({"what": "device-resident run vs the recorded digests of an oracle-verified run of the same inputs", "vs": "recorded:" + exp_src,
+                       "scale": a.scale, "identical": exp == dig_dev})
 
     # dominant kernel: k_fasta_emit.  Algorithmic bytes = sequence bytes gathered + FASTA bytes written.
     frag = ctx.table(api.TAB_FRAG).reshape(-1, 3)
     gathered = int((frag[:, 2].astype(np.int64) - frag[:, 1]).sum())
+    del frag
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -270,7 +397,7 @@ def ours(a):
     ach = alg_fasta / (fasta_ms / a.steps / 1e3) / 1e9 if fasta_ms else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_fasta_emit_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_fasta_emit_bytes_per_launch") if a.config == "C2" else None
     except Exception:
         pass
     roofline = {"kernel": "k_fasta_emit", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
@@ -280,6 +407,8 @@ def ours(a):
     paf_bytes = int(ds.paf.numel())
     bytes_alg = paf_bytes + gathered + int(ds.names.numel()) + sum(out_bytes)
     path_roof = {"bytes_alg": bytes_alg, "achieved_gbs": bytes_alg / (ms_step / 1e3) / 1e9, "frac": bytes_alg / (ms_step / 1e3) / 1e9 / peak}
+    sizes = {"n_overlaps": n_ovl, "n_reads": ds.n, "bases": ds.bases, "paf_bytes": paf_bytes, "genome": ds.meta["genome"],
+             "out_bytes": {"coverage.txt": out_bytes[0], "long_repeats.txt": out_bytes[1], "reads.fasta": out_bytes[3]}, **stats_line}
 
     # ---- row f2: device FASTA ingest of the same reads (unwrapped FASTA text generated chunk by chunk in HBM; only the
     # raftgpu_ingest_fasta calls are timed, CUDA events around each)
@@ -299,7 +428,7 @@ def ours(a):
                 seq_keep = None
                 torch.cuda.empty_cache()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for timed in (False, True):  # first pass untimed: it pays the one-time cudaMalloc of the ~100 GB arena
+            for timed in (False, True):  # first pass untimed: it pays the one-time cudaMalloc of the arena
                 if timed:
                     ctxf.reset()
                 ms_f = 0.0
@@ -312,7 +441,6 @@ def ours(a):
                     f1.record()
                     torch.cuda.synchronize()
                     ms_f += f0.elapsed_time(f1)
-            ok = ctxf.stats().n_reads == 0  # stats are filled by run(); check the read count through a table instead
             nb_off = ctxf.table(api.TAB_BIN_OFF)
             fasta_ingest = {"text_bytes": total_text, "ms": ms_f, "gbs_text": total_text / (ms_f / 1e3) / 1e9,
                             "alg_gbs": (total_text + ds.bases) / (ms_f / 1e3) / 1e9, "reads": int(len(nb_off) - 1),
@@ -327,20 +455,22 @@ def ours(a):
             log(f"[bench] fasta ingest measurement failed: {e}")
             ctx = api.Context(p, local)
 
-    # ---- e2e: pinned host inputs -> C ABI -> host outputs
-    e2e = None
-    if not a.no_e2e and not host_can_hold(sum(int(t.numel() * t.element_size()) for t in (ds.seq_off, ds.name_off, ds.seq, ds.names, ds.paf))):
-        log("[bench] host memory too small to pin the inputs of this workload: e2e skipped")
-        a.no_e2e = True
-    if not a.no_e2e:
-        def pinned(t):  # straight into pinned memory (no pageable intermediate copy)
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    # ---- host copies of the inputs: pinned for the e2e leg, and what the oracle reads for the full-size parity check
+    in_bytes = sum(int(t.numel() * t.element_size()) for t in (ds.seq_off, ds.name_off, ds.seq, ds.names, ds.paf))
+    want_host = not (a.no_e2e and a.no_oracle)
+    if want_host and host_available() < in_bytes + (40 << 30):
+        log("[bench] host memory too small to hold the inputs of this workload: e2e and the full-size oracle check are skipped")
+        want_host = False
+    e2e, oracle_info = None, None
+    if want_host:
+        def to_host(t, pin):  # straight into pinned memory (no pageable intermediate copy)
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
             h.copy_(t)
             return h
-        hseq_off, hname_off = pinned(ds.seq_off), pinned(ds.name_off)
-        hseq, hnames, hpaf = pinned(ds.seq), pinned(ds.names), pinned(ds.paf)
-        hout = torch.empty(WINDOW, dtype=torch.uint8, pin_memory=True)
-        h2d = sum(int(t.numel() * t.element_size()) for t in (hseq_off, hname_off, hseq, hnames, hpaf))
+        pin = not a.no_e2e
+        hseq_off, hname_off = to_host(ds.seq_off, pin), to_host(ds.name_off, pin)
+        hseq, hnames, hpaf = to_host(ds.seq, pin), to_host(ds.names, pin), to_host(ds.paf, pin)
+        ds_args, ds_n, ds_bases = ds.args, ds.n, ds.bases
         # the library now needs its own copy of the inputs in HBM: drop the device-resident set and its context
         ctx.close()
         ds.seq = ds.paf = ds.names = ds.seq_off = ds.name_off = None
@@ -348,82 +478,98 @@ def ours(a):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        log(f"[bench] e2e: torch holds {torch.cuda.memory_reserved() / 1e9:.1f} GB of HBM after releasing the resident inputs")
-        ctx = api.Context(p, local)
+        if not a.no_e2e:
+            hout = torch.empty(WINDOW, dtype=torch.uint8, pin_memory=True)
+            log(f"[bench] e2e: torch holds {torch.cuda.memory_reserved() / 1e9:.1f} GB of HBM after releasing the resident inputs")
+            ctx = api.Context(p, local)
+            # the read arena is uploaded in chunks behind the PAF, overlapping the kernels and the D2H of the outputs
+            ctx.set_option(api.OPT_DEFER_SEQ_UPLOAD, 1)
 
-        # the read arena is uploaded in chunks behind the PAF, overlapping the kernels and the D2H of the outputs
-        ctx.set_option(api.OPT_DEFER_SEQ_UPLOAD, 1)
+            def step_e2e():
+                ctx.set_reads(hseq_off.numpy(), hseq.numpy(), hname_off.numpy(), hnames.numpy())
+                ctx.ingest_paf(hpaf.numpy(), hpaf.numel(), last=True)
+                ctx.run()
+                d2h = 0
+                for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+                    n = ctx.output_size(which)
+                    for off in range(0, n, WINDOW):
+                        ctx.fetch_into(which, off, hout.data_ptr(), min(WINDOW, n - off))
+                    d2h += n
+                return d2h
 
-        def step_e2e():
-            ctx.set_reads(hseq_off.numpy(), hseq.numpy(), hname_off.numpy(), hnames.numpy())
-            ctx.ingest_paf(hpaf.numpy(), hpaf.numel(), last=True)
-            ctx.run()
-            d2h = 0
-            for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
-                n = ctx.output_size(which)
-                for off in range(0, n, WINDOW):
-                    ctx.fetch_into(which, off, hout.data_ptr(), min(WINDOW, n - off))
-                d2h += n
-            return d2h
-
-        step_e2e()
-        torch.cuda.synchronize()
-        k = max(1, min(a.steps, 3))
-        e0.record()
-        for _ in range(k):
-            d2h = step_e2e()
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e2e = e0.elapsed_time(e1) / k
-        e2e = {"value": n_ovl / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-               "steps": k}
-        del hseq, hpaf, hout
-
-    # ---- cpu baseline (rank 0, bounded sample) + parity of the same sample through the CUDA path
-    cpu = None
-    if not a.no_cpu:
-        from oracle import oracle as O
-        ctx.close()  # release HBM before the sample is generated and checked
-        torch.cuda.empty_cache()
-        reads, paf, args, n_s, scale = make_sample(a.config, 4.0e6, OVL_PER_UNIT[a.config])
-        d = tempfile.mkdtemp(prefix="raft_cpu_")
-        try:
-            fa, pf = write_sample_files(d, reads, paf)
-            if O.have_ref():
-                own, wall, n = run_reference_once(O.REF_BIN, fa, pf, args, d)
-                kind = "reference"
-                outs = {s: open(os.path.join(d, "ref." + s), "rb").read() for s in ("coverage.txt", "long_repeats.txt", "reads.fasta")}
+            step_e2e()
+            torch.cuda.synchronize()
+            k = max(1, min(a.steps, 3))
+            e0.record()
+            for _ in range(k):
+                d2h = step_e2e()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_e2e = e0.elapsed_time(e1) / k
+            e2e = {"value": n_ovl / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                   "steps": k}
+            # parity, part 2: the state the host-fed run left on the device digests to the same three files
+            dig_e2e = device_digests(ctx, api)
+            checks.append({"what": "e2e run (pinned host inputs through the C ABI) vs the device-resident run", "vs": "n1", "scale": a.scale,
+                           "identical": dig_e2e == dig_dev})
+            ctx.close()
+            del hout
+            torch.cuda.empty_cache()
+        # parity, part 3: the CPU oracle on the very same full-size inputs (every host core), outputs as digests
+        if not a.no_oracle:
+            # the oracle keeps 4 B per coverage slot, 24 B per record (twice while the ranges are concatenated) and the name map
+            if host_available() > 4 * (int(st.n_bins) + ds_n) + 56 * n_ovl + (12 << 30):
+                class _R:
+                    pass
+                rd = _R()
+                rd.seq_off, rd.seq, rd.name_off, rd.names = hseq_off.numpy(), hseq.numpy(), hname_off.numpy(), hnames.numpy()
+                threads = os.cpu_count() or 1
+                dig_orc, dt, r = oracle_digests(rd, hpaf.numpy(), ds_args, threads)
+                ok = dig_orc == dig_dev and (r.n_rec, r.symmetric, r.high_cov, r.n_frag, r.n_rep) == (n_ovl, st.symmetric, st.high_cov, st.n_fragments, st.n_repeats)
+                checks.append({"what": "device-resident run vs the CPU oracle (oracle/orc_run_digest) on the same full-size inputs", "vs": "oracle",
+                               "scale": a.scale, "identical": bool(ok), "oracle_seconds": dt, "oracle_threads": threads})
+                oracle_info = {"seconds": dt, "threads": threads, "overlaps_per_s": n_ovl / dt}
+                if ok:
+                    save_digests(key, dig_dev)
+                else:
+                    log(f"[bench] PARITY FAILURE vs oracle: device {dig_dev} oracle {dig_orc}")
             else:
-                t0 = time.perf_counter()
-                res = O.run(reads, paf, O.make_params(**_kw(args)))
-                own = wall = time.perf_counter() - t0
-                kind = "port"
-                outs = {"coverage.txt": res.cov_txt, "long_repeats.txt": res.rep_txt, "reads.fasta": res.fasta}
-            c2 = api.Context(api.AlgoParams.from_args(args), local)
-            c2.set_reads(reads.seq_off, reads.seq, reads.name_off, reads.names)
-            c2.ingest_paf(np.frombuffer(paf, np.uint8), len(paf), last=True)
-            c2.run()
-            same = all(c2.digest(w) == O.digest(outs[s]) and c2.output_size(w) == len(outs[s]) for w, s in
-                       ((api.OUT_COVERAGE, "coverage.txt"), (api.OUT_LONG_REPEATS, "long_repeats.txt"), (api.OUT_READS_FASTA, "reads.fasta")))
-            c2.close()
-            cpu = {"value": n_s / wall, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(), "seconds": wall,
-                   "reference_own_timer_s": own, "gbp_per_s": int(reads.seq_off[-1]) / wall / 1e9,
-                   "sample": f"{a.config}-shaped at genome scale {scale:.4g}: {n_s} overlaps, {int(reads.seq_off[-1])} bases, file to file",
-                   "gpu_outputs_identical_on_sample": bool(same)}
-        finally:
-            shutil.rmtree(d, ignore_errors=True)
+                log("[bench] not enough free host memory for the full-size oracle run")
+        del hseq, hpaf, hseq_off, hname_off, hnames
+        gc.collect()
+        try:
+            torch._C._host_emptyCache()  # hand the pinned input copies back to the OS: the file leg wants the RAM as tmpfs
+        except Exception:
+            pass
+    else:
+        ctx.close()
 
+    # ---- file -> file: our CLI and the unmodified reference on the same sample files; the reference's time is the CPU baseline
+    cpu, f2f = None, None
+    if not a.no_cpu:
+        torch.cuda.empty_cache()
+        f2f = file_to_file_leg(a, local, log)
+        if f2f is not None:
+            checks.append({"what": "raft_b200/raft vs the unmodified reference binary, file to file, four output files compared byte by byte",
+                           "vs": "reference", "scale": a.scale / SAMPLE_DIV[a.config], "identical": f2f["identical"]})
+            cpu = {"value": f2f["reference"]["overlaps_per_s"], "unit": UNIT, "cores": 1, "kind": "reference", "host_cores": os.cpu_count(),
+                   "seconds": f2f["reference"]["wall_s"], "reference_own_timer_s": f2f["reference"]["t_file_s"],
+                   "gbp_per_s": f2f["reference"]["gbp_per_s"], "sample": f2f["sample"], "gpu_outputs_identical_on_sample": f2f["identical"]}
+
+    best = next((c for c in checks if c["vs"] == "oracle"), None) or next((c for c in checks if c["vs"] == "reference"), None) or (checks[0] if checks else None)
+    parity = {"identical": all(c["identical"] for c in checks) if checks else None, "scale": best["scale"] if best else None,
+              "vs": best["vs"] if best else None, "digests": dig_dev, "checks": checks}
+    cfg = config_block(a, ds.args if ds.args else [])
     out = {"metric": METRIC, "value": n_ovl / (ms_step / 1e3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
-           "config": {"workload": f"{a.config} synthetic human 32x ONT-Duplex-shaped reads + symmetric all-vs-all PAF, genome scale {a.scale:g} "
-                                  f"({ds.meta['genome'] / 1e9:.2f} Gbp genome; raft {' '.join(ds.args)}, defaults -r 50 -l 20000), 1 B200", "n_overlaps": n_ovl, "n_reads": ds.n, "bases": ds.bases,
-                      "paf_bytes": paf_bytes, "out_bytes": {"coverage.txt": out_bytes[0], "long_repeats.txt": out_bytes[1],
-                                                                      "reads.fasta": out_bytes[3]},
-                      "l2": "inputs and outputs are GBs (>> 126 MB L2); no explicit flush", "sharding": "none (1 GPU)"},
-           "gbp_per_s": ds.bases / (ms_step / 1e3) / 1e9, "stage_ms": stage, "roofline": roofline, "path_roofline": path_roof,
-           "cpu_baseline": cpu, "e2e": e2e, "fasta_ingest": fasta_ingest, "gpu_launches": launches, "clocks": clk}
+           "config": cfg, "workload_sizes": sizes, "sharding": "none (1 GPU)",
+           "gbp_per_s": sizes["bases"] / (ms_step / 1e3) / 1e9, "stage_ms": stage, "roofline": roofline, "path_roofline": path_roof,
+           "parity": parity, "file_to_file": f2f, "cpu_baseline": cpu, "oracle_full_scale": oracle_info, "e2e": e2e, "fasta_ingest": fasta_ingest,
+           "gpu_launches": launches, "clocks": clk}
     print(json.dumps(out), flush=True)
-    ctx.close()
+    if parity["identical"] is False:
+        log("[bench] PARITY CHECK FAILED: " + json.dumps(checks))
+        sys.exit(3)
 
 
 def main():
@@ -438,10 +584,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2")
-    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the config (1.0 = the full human-scale config)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIG_DESC))
+    ap.add_argument("--asymmetric", action="store_true", help="one PAF record per overlapping pair (every target side is then routed / scattered)")
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale of the config (1.0 = the full config)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the file -> file leg (our CLI + the reference binary on the sample files)")
+    ap.add_argument("--no-oracle", action="store_true", help="skip the full-size CPU oracle parity check")
     ap.add_argument("--no-fasta", action="store_true", help="skip the device FASTA ingest side measurement")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

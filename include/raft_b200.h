@@ -51,7 +51,8 @@ typedef enum {
     RAFTGPU_E_IO = -10,          /* input file missing or empty (chop.hpp:336-349) / write failure */
     RAFTGPU_E_ARG = -11,         /* bad argument */
     RAFTGPU_E_UNSUPPORTED = -12,
-    RAFTGPU_E_SIM_NAME = -13     /* simulated-read mode (chop.hpp:99-106) but a name lacks the fields chop.hpp:14-70 dereference */
+    RAFTGPU_E_SIM_NAME = -13,    /* simulated-read mode (chop.hpp:99-106) but a name lacks the fields chop.hpp:14-70 dereference */
+    RAFTGPU_E_PEER = -14         /* sharded run: this rank is fine, another rank reported an error */
 } raftgpu_status;
 
 /* Output streams (files the reference writes: chop.hpp:333, repeat.hpp:85-87). */
@@ -163,6 +164,9 @@ int raftgpu_sync(raftgpu_ctx *ctx);
 /* Order-independent 64-bit digest of a whole output stream computed on the device
  * (sum over bytes of mix64(offset*257 + byte + 1)); used for parity at sizes the host cannot hold. */
 int raftgpu_digest(raftgpu_ctx *ctx, int which, uint64_t *digest);
+/* Same with the context's stream placed at byte `stream_base` of a larger file: a rank of a sharded run digests its
+ * slice at its file offset, and the per-rank digests add up (mod 2^64) to the digest of the whole file. */
+int raftgpu_digest_at(raftgpu_ctx *ctx, int which, uint64_t stream_base, uint64_t *digest);
 /* Copies an integer table to dst [host|device]; *n_elems receives the element count (call with
  * dst=NULL to size). */
 int raftgpu_fetch_table(raftgpu_ctx *ctx, int table, void *dst, size_t cap_bytes, size_t *n_elems);
@@ -173,9 +177,54 @@ int raftgpu_fetch_table(raftgpu_ctx *ctx, int table, void *dst, size_t cap_bytes
  * as stream RAFTGPU_OUT_SPLIT_NAIVE through raftgpu_output_size / raftgpu_fetch / raftgpu_digest (same gather kernel). */
 int raftgpu_split_naive(raftgpu_ctx *ctx, int32_t subread_length);
 
-/* ---- multi-GPU (one context per rank; the exchange itself is done by the caller, e.g. NCCL
- * all-to-all over NVLink).  Reads are partitioned into contiguous id ranges; every rank holds all
- * names and lengths, and sequence bytes for its own range only. */
+/* ---- multi-GPU inside the library: one context per GPU ("rank"), reads partitioned into contiguous id ranges
+ * (bounds[nranks+1]), every rank holding all names + lengths (raftgpu_set_reads_sharded) and its own share of the PAF
+ * text (any line-complete part of the file; the rank holding the file's first line must be rank 0 or the ranks
+ * before it must hold no record).  The ranks may be threads of one process (the `raft` CLI with RAFT_B200_DEVICES)
+ * or processes (bench.py under torchrun): they share an NCCL communicator built from one 128-byte id.
+ *
+ * raftgpu_run_sharded is raftgpu_ingest_paf + raftgpu_run for a rank.  Its exchange steps, all on the context's
+ * stream, NCCL over NVLink: record 0 of the file (chop.hpp:171-184) = all-gather of every rank's first record;
+ * symmetric flag = all-reduce(max); each contributing interval on a read another rank owns (chop.hpp:165-169)
+ * = one 12-byte endpoint, counts all-gathered, endpoints exchanged with grouped ncclSend / ncclRecv; global `read=`
+ * numbering (chop.hpp:195,266,319) = all-gather of fragment counts; file offsets of the rank's output slices =
+ * all-gather of output sizes.  Afterwards raftgpu_output_size / raftgpu_fetch / raftgpu_digest_at serve this rank's
+ * slice of every output file; info->stream_base[w] is where it starts in file w. */
+#define RAFTGPU_COMM_ID_BYTES 128
+typedef struct {
+    int32_t  nranks, rank;
+    int32_t  symmetric, reserved;
+    int64_t  n_records_total, n_fragments_total, first_read_num;
+    int64_t  endpoints_sent, endpoints_received; /* 12-byte endpoints this rank sent to / received from other ranks */
+    uint64_t stream_base[4], stream_total[4];    /* indexed by RAFTGPU_OUT_*: file offset of this rank's slice, whole file size */
+    int64_t  total_cov, total_repeat_len, total_read_len, n_bins_total; /* sums over ranks, for the stdout lines (repeat.hpp:173-178) */
+    float    ms_exchange;                        /* device time of route count + pack + send/recv + scatter of the received endpoints */
+    int32_t  peek_retries;
+} raftgpu_shard_info;
+int raftgpu_comm_unique_id(uint8_t id[RAFTGPU_COMM_ID_BYTES]);
+/* collective over the ranks: every rank calls it with the same id and nranks, its own rank */
+int raftgpu_comm_init(raftgpu_ctx *ctx, int nranks, int rank, const uint8_t id[RAFTGPU_COMM_ID_BYTES]);
+int raftgpu_comm_destroy(raftgpu_ctx *ctx);
+int raftgpu_run_sharded(raftgpu_ctx *ctx, const int64_t *bounds /* nranks+1 */, const uint8_t *text /* [host|device] */, size_t nbytes,
+                        raftgpu_stats *stats, raftgpu_shard_info *info);
+/* The same in three steps for a rank whose text arrives in chunks (files larger than memory): begin with the first chunk
+ * (record 0 of the file is looked for in it; head_is_whole_text=1 when it is the rank's only chunk), raftgpu_ingest_paf
+ * for every chunk including the first, then finish.  A data error of an ingest call is carried into finish so that every
+ * rank still meets the others in the collectives (the failing rank gets its own code back, the others RAFTGPU_E_PEER). */
+int raftgpu_sharded_begin(raftgpu_ctx *ctx, const int64_t *bounds, const uint8_t *head_text, size_t head_bytes, int head_is_whole_text);
+int raftgpu_sharded_finish(raftgpu_ctx *ctx, raftgpu_stats *stats, raftgpu_shard_info *info);
+/* Reads held by a context (after raftgpu_ingest_fasta / raftgpu_set_reads[_sharded]): how many it owns, then host copies of
+ * their names (offsets relative to the first owned name) and lengths, and the device pointers of its sequence arena --
+ * what a multi-GPU caller needs to turn per-rank FASTA ingests into one raftgpu_set_reads_sharded per rank. */
+int raftgpu_reads_info(raftgpu_ctx *ctx, int64_t *n_local, int64_t *name_bytes, int64_t *seq_bytes);
+int raftgpu_reads_copy(raftgpu_ctx *ctx, int64_t *name_off /* n_local+1 */, uint8_t *names, int64_t *lengths /* n_local */);
+int raftgpu_reads_device(raftgpu_ctx *ctx, const int64_t **seq_off_device, const uint8_t **seq_device);
+/* Read-id range boundaries balanced by coverage slots (ceil(L/reso) + 1 per read): bounds[nranks+1]. lengths [host]. */
+int raftgpu_partition_reads(const int64_t *lengths, int64_t n, int32_t reso, int nranks, int64_t *bounds);
+
+/* ---- multi-GPU building blocks for callers that run the exchange themselves (one context per rank).  Reads are
+ * partitioned into contiguous id ranges; every rank holds all names and lengths, and sequence bytes for its own
+ * range only. */
 int raftgpu_set_reads_sharded(raftgpu_ctx *ctx, int64_t n, const int64_t *lengths /* int64[n] */,
                               const int64_t *name_off, const uint8_t *names, int64_t own_first,
                               int64_t own_count, const int64_t *own_seq_off /* own_count+1, local */,
@@ -212,6 +261,11 @@ int raftgpu_break_long_reads(const char *readfilename, const char *paffilename, 
  * buffers by a reader thread so file reading overlaps the device tokenizer.  n_paf >= 1. */
 int raftgpu_break_long_reads_multi(const char *readfilename, int n_paf, const char *const *paffilenames,
                                    const raftgpu_params *p, const char *prefix, int device, raftgpu_stats *stats_out);
+/* Same over several GPUs of this box (one host thread + context per device, raftgpu_run_sharded underneath): reads
+ * sharded by id range, every PAF file cut into byte ranges at line ends, each rank writing its slice of the four output
+ * files at its file offset.  Files and stdout lines are identical to the single-GPU call. */
+int raftgpu_break_long_reads_mgpu(const char *readfilename, int n_paf, const char *const *paffilenames, const raftgpu_params *p,
+                                  const char *prefix, int ndev, const int *devices, raftgpu_stats *stats_out);
 
 #ifdef __cplusplus
 }

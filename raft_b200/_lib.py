@@ -10,11 +10,13 @@ LIB_PATH = os.path.join(HERE, "libraft_b200.so")
 SYMBOLS = [
     "raftgpu_default_params", "raftgpu_create", "raftgpu_destroy", "raftgpu_reset", "raftgpu_strerror",
     "raftgpu_last_error", "raftgpu_error_index", "raftgpu_set_option", "raftgpu_set_reads", "raftgpu_ingest_fasta", "raftgpu_load_fasta", "raftgpu_free_host",
-    "raftgpu_split_naive", "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_fetch_async", "raftgpu_sync", "raftgpu_digest",
+    "raftgpu_split_naive", "raftgpu_ingest_paf", "raftgpu_run", "raftgpu_get_stats", "raftgpu_output_size", "raftgpu_fetch", "raftgpu_fetch_async", "raftgpu_sync", "raftgpu_digest", "raftgpu_digest_at",
     "raftgpu_fetch_table", "raftgpu_set_reads_sharded", "raftgpu_peek_first_record", "raftgpu_set_first_record",
     "raftgpu_get_symmetric", "raftgpu_set_symmetric", "raftgpu_route_count", "raftgpu_route_pack",
     "raftgpu_accumulate_local", "raftgpu_accumulate_endpoints", "raftgpu_finalize", "raftgpu_set_output_base", "raftgpu_break_long_reads",
-    "raftgpu_break_long_reads_multi",
+    "raftgpu_break_long_reads_multi", "raftgpu_comm_unique_id", "raftgpu_comm_init", "raftgpu_comm_destroy", "raftgpu_run_sharded",
+    "raftgpu_partition_reads", "raftgpu_break_long_reads_mgpu", "raftgpu_sharded_begin", "raftgpu_sharded_finish",
+    "raftgpu_reads_info", "raftgpu_reads_copy", "raftgpu_reads_device",
 ]
 
 
@@ -37,6 +39,17 @@ class Stats(C.Structure):
                 ("ms_set_reads", C.c_float), ("reserved2", C.c_int32)]
 
 
+class ShardInfo(C.Structure):
+    """raftgpu_shard_info"""
+    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("symmetric", C.c_int32), ("reserved", C.c_int32),
+                ("n_records_total", C.c_int64), ("n_fragments_total", C.c_int64), ("first_read_num", C.c_int64),
+                ("endpoints_sent", C.c_int64), ("endpoints_received", C.c_int64),
+                ("stream_base", C.c_uint64 * 4), ("stream_total", C.c_uint64 * 4),
+                ("total_cov", C.c_int64), ("total_repeat_len", C.c_int64), ("total_read_len", C.c_int64), ("n_bins_total", C.c_int64),
+                ("ms_exchange", C.c_float), ("peek_retries", C.c_int32)]
+
+
+COMM_ID_BYTES = 128
 _lib = None
 
 
@@ -72,6 +85,7 @@ def lib():
         "raftgpu_fetch_async": (C.c_int, [vp, C.c_int, u64, vp, sz]),
         "raftgpu_sync": (C.c_int, [vp]),
         "raftgpu_digest": (C.c_int, [vp, C.c_int, C.POINTER(u64)]),
+        "raftgpu_digest_at": (C.c_int, [vp, C.c_int, u64, C.POINTER(u64)]),
         "raftgpu_fetch_table": (C.c_int, [vp, C.c_int, vp, sz, C.POINTER(sz)]),
         "raftgpu_set_reads_sharded": (C.c_int, [vp, i64, vp, vp, vp, i64, i64, vp, vp]),
         "raftgpu_peek_first_record": (C.c_int, [vp, vp, sz, C.POINTER(i32 * 6), C.POINTER(i32)]),
@@ -86,6 +100,17 @@ def lib():
         "raftgpu_set_output_base": (C.c_int, [vp, i64]),
         "raftgpu_break_long_reads": (C.c_int, [C.c_char_p, C.c_char_p, PP, C.c_char_p, C.c_int, PS]),
         "raftgpu_break_long_reads_multi": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), PP, C.c_char_p, C.c_int, PS]),
+        "raftgpu_comm_unique_id": (C.c_int, [vp]),
+        "raftgpu_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "raftgpu_comm_destroy": (C.c_int, [vp]),
+        "raftgpu_run_sharded": (C.c_int, [vp, vp, vp, sz, PS, C.POINTER(ShardInfo)]),
+        "raftgpu_partition_reads": (C.c_int, [vp, i64, i32, C.c_int, vp]),
+        "raftgpu_sharded_begin": (C.c_int, [vp, vp, vp, sz, C.c_int]),
+        "raftgpu_sharded_finish": (C.c_int, [vp, PS, C.POINTER(ShardInfo)]),
+        "raftgpu_reads_info": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "raftgpu_reads_copy": (C.c_int, [vp, vp, vp, vp]),
+        "raftgpu_reads_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "raftgpu_break_long_reads_mgpu": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), PP, C.c_char_p, C.c_int, C.POINTER(C.c_int), PS]),
     }
     for name in SYMBOLS:
         fn = getattr(L, name)  # AttributeError if the symbol is not exported

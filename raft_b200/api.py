@@ -73,8 +73,10 @@ def _ptr(a):
         return a
     if isinstance(a, np.ndarray):
         return a.ctypes.data if a.size else None
-    if isinstance(a, (bytes, bytearray)):
-        return C.cast(C.c_char_p(bytes(a)), C.c_void_p).value if len(a) else None
+    if isinstance(a, bytes):
+        return C.cast(C.c_char_p(a), C.c_void_p).value if len(a) else None  # the bytes object itself (kept alive by the caller)
+    if isinstance(a, bytearray):
+        return C.addressof((C.c_char * len(a)).from_buffer(a)) if len(a) else None  # in place, no temporary copy
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
     raise TypeError(type(a))
@@ -113,9 +115,15 @@ class Context:
 
     # ---- a0 loadFASTA (chop.hpp:88-131), after tokenisation
     def set_reads(self, seq_off, seq, name_off, names):
-        self._keep = [seq_off, seq, name_off, names]
+        # the previous inputs stay referenced until the C call has returned: it starts with raftgpu_reset, which waits for
+        # a deferred upload that may still be reading the old host arena
+        old, new = self._keep, [seq_off, seq, name_off, names]
         n = len(seq_off) - 1
-        self._ck(self.L.raftgpu_set_reads(self._h, n, _ptr(seq_off), _ptr(seq), _ptr(name_off), _ptr(names)))
+        try:
+            self._ck(self.L.raftgpu_set_reads(self._h, n, _ptr(seq_off), _ptr(seq), _ptr(name_off), _ptr(names)))
+        finally:
+            self._keep = new
+            del old
 
     def ingest_fasta(self, text, nbytes=None, last=True, total_hint=0):
         """Device FASTA tokenizer (loadFASTA's record grammar, chop.hpp:88-131); raises RaftError(-12) for FASTQ / CRLF text."""
@@ -125,9 +133,13 @@ class Context:
         self._ck(self.L.raftgpu_ingest_fasta(self._h, _ptr(text), nbytes, 1 if last else 0, total_hint))
 
     def set_reads_sharded(self, n, lengths, name_off, names, own_first, own_count, own_seq_off, own_seq):
-        self._keep = [lengths, name_off, names, own_seq_off, own_seq]
-        self._ck(self.L.raftgpu_set_reads_sharded(self._h, n, _ptr(lengths), _ptr(name_off), _ptr(names), own_first,
-                                                  own_count, _ptr(own_seq_off), _ptr(own_seq)))
+        old, new = self._keep, [lengths, name_off, names, own_seq_off, own_seq]
+        try:
+            self._ck(self.L.raftgpu_set_reads_sharded(self._h, n, _ptr(lengths), _ptr(name_off), _ptr(names), own_first,
+                                                      own_count, _ptr(own_seq_off), _ptr(own_seq)))
+        finally:
+            self._keep = new
+            del old
 
     def split_naive(self, subread_length: int):
         """split_naive.cpp:10-44 on the device; bytes through fetch(OUT_SPLIT_NAIVE)."""
@@ -183,9 +195,11 @@ class Context:
     def sync(self):
         self._ck(self.L.raftgpu_sync(self._h))
 
-    def digest(self, which) -> int:
+    def digest(self, which, stream_base=0) -> int:
+        """64-bit digest of a whole output stream, computed on the device; `stream_base` = file offset of this
+        context's slice when the run is sharded (per-rank digests then add up to the file's)."""
         d = C.c_uint64()
-        self._ck(self.L.raftgpu_digest(self._h, which, C.byref(d)))
+        self._ck(self.L.raftgpu_digest_at(self._h, which, stream_base, C.byref(d)))
         return d.value
 
     def table(self, tab) -> np.ndarray:
@@ -196,7 +210,26 @@ class Context:
             self._ck(self.L.raftgpu_fetch_table(self._h, tab, out.ctypes.data, out.nbytes, C.byref(n)))
         return out
 
-    # ---- multi-GPU plumbing
+    # ---- multi-GPU inside the library (NCCL): raftgpu_comm_init + raftgpu_run_sharded
+    def comm_init(self, nranks, rank, comm_id: bytes):
+        """Collective over the ranks: the same 128-byte id (comm_unique_id() of one rank) everywhere."""
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._ck(self.L.raftgpu_comm_init(self._h, nranks, rank, C.addressof(buf)))
+
+    def comm_destroy(self):
+        self._ck(self.L.raftgpu_comm_destroy(self._h))
+
+    def run_sharded(self, bounds: np.ndarray, text, nbytes=None):
+        """raftgpu_ingest_paf + raftgpu_run for one rank of a sharded run; returns (stats, shard_info)."""
+        if nbytes is None:
+            nbytes = len(text) if not hasattr(text, "numel") else text.numel()
+        self._keep.append(text)
+        bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+        s, info = _lib.Stats(), _lib.ShardInfo()
+        self._ck(self.L.raftgpu_run_sharded(self._h, bounds.ctypes.data, _ptr(text), nbytes, C.byref(s), C.byref(info)))
+        return s, info
+
+    # ---- multi-GPU building blocks (the caller runs the exchange)
     def peek_first_record(self, text, nbytes):
         rec, found = (C.c_int32 * 6)(), C.c_int32()
         self._ck(self.L.raftgpu_peek_first_record(self._h, _ptr(text), nbytes, C.byref(rec), C.byref(found)))
@@ -233,6 +266,25 @@ class Context:
         self._ck(self.L.raftgpu_set_output_base(self._h, first_read_num))
 
 
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library: created by one rank, handed to every rank's Context.comm_init."""
+    buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+    st = _lib.lib().raftgpu_comm_unique_id(C.addressof(buf))
+    if st:
+        raise RaftError(st, "raftgpu_comm_unique_id")
+    return bytes(buf)
+
+
+def partition_reads(lengths, reso, nranks) -> np.ndarray:
+    """Read-id range boundaries (int64[nranks+1]) balanced by coverage slots (raftgpu_partition_reads)."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    bounds = np.zeros(nranks + 1, dtype=np.int64)
+    st = _lib.lib().raftgpu_partition_reads(lengths.ctypes.data, len(lengths), reso, nranks, bounds.ctypes.data)
+    if st:
+        raise RaftError(st, "raftgpu_partition_reads")
+    return bounds
+
+
 def load_fasta(path):
     """loadFASTA's record reader (chop.hpp:88-131 / kseq.h:240-298) -> (seq_off, seq, name_off, names)."""
     L = _lib.lib()
@@ -253,15 +305,23 @@ def load_fasta(path):
     return seq_off, seq, name_off, names
 
 
-def break_long_reads(readfilename: str, paffilename, params: AlgoParams, device: int = 0):
+def break_long_reads(readfilename: str, paffilename, params: AlgoParams, device=0):
     """Drop-in for break_long_reads (chop.hpp:331-373): files in, prefix.* files out.
 
     `paffilename` may be a list of paths: they are ingested back to back as `cat` would join them
-    (README.md:35-36 merges hifiasm's *.0.ovlp.paf and *.1.ovlp.paf before calling raft)."""
+    (README.md:35-36 merges hifiasm's *.0.ovlp.paf and *.1.ovlp.paf before calling raft).
+    `device` may be a list of GPU indices: the run is then sharded over them (raftgpu_break_long_reads_mgpu)."""
     L = _lib.lib()
     s = _lib.Stats()
     pafs = [paffilename] if isinstance(paffilename, (str, bytes)) else list(paffilename)
     arr = (C.c_char_p * len(pafs))(*[q.encode() if isinstance(q, str) else q for q in pafs])
+    if isinstance(device, (list, tuple)):
+        devs = (C.c_int * len(device))(*device)
+        st = L.raftgpu_break_long_reads_mgpu(readfilename.encode(), len(pafs), arr, C.byref(params.c_struct()),
+                                             params.outputfilename.encode(), len(device), devs, C.byref(s))
+        if st:
+            raise RaftError(st)
+        return s
     st = L.raftgpu_break_long_reads_multi(readfilename.encode(), len(pafs), arr, C.byref(params.c_struct()),
                                           params.outputfilename.encode(), device, C.byref(s))
     if st:

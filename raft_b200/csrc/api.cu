@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/raft_b200.h"
 #include "kernels.h"
 
@@ -62,6 +64,7 @@ struct Misc {
     int                fa_flags;
     int                fa_pad;
     long long          fa_totals[3];
+    long long          zero;     // stays 0 (a size that does not exist on this run, for the packed all-gathers)
 };
 
 constexpr size_t WINDOW_BYTES = 256ull << 20; // staging window for host fetches
@@ -95,7 +98,8 @@ struct raftgpu_ctx {
     int64_t rec_cap = 0, n_rec = 0;
     DevBuf  b_text;
     std::vector<uint8_t> carry;
-    bool    first_is_local = true, rec0_external = false, sym_external = false, paf_done = false;
+    int     first_is_local = 1; // 1 / 0, or -1: the tokenizer reads it from rec0[7] on the device (sharded runs)
+    bool    rec0_external = false, sym_external = false, paf_done = false;
     bool    q_scattered = false; // query sides went into the difference array during tokenisation
     int     h_sym = 0;           // host copy of the (local) symmetric flag after the last ingest
     int64_t paf_bytes = 0;
@@ -115,7 +119,7 @@ struct raftgpu_ctx {
     int64_t G = 0, n_repeats = 0, read_num_base = 0;
     raftgpu_stats stats{};
     DevBuf  b_stage[2];
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[10]{};
     cudaEvent_t ev_stage[2]{};
     // two emit lanes so that the issue-bound text emitters and the bandwidth-bound gather can overlap:
     // lane 0 (stream st_aux): coverage.txt, long_repeats.txt, .bed;  lane 1 (stream st): reads.fasta, split_naive
@@ -148,7 +152,36 @@ struct raftgpu_ctx {
     size_t         n_chunks = 0;
     std::vector<int64_t> h_frag_sample;  // (out_off, src_off) of every FRAG_SAMPLE-th record
     DevBuf         b_frag_sample;
+
+    // sharded runs inside the library (raftgpu_comm_init / raftgpu_run_sharded): NCCL over NVLink
+    ncclComm_t     comm = nullptr;
+    int            nranks = 1, rank = 0;
+    bool           gather_on = false;    // finalize / layout add their all-gathers (set while raftgpu_run_sharded runs)
+    DevBuf         b_coll, b_send, b_recv, b_peek;
+    long long*     h_coll = nullptr;     // pinned host mirror of the gathered words
+    raftgpu_shard_info shard{};
+    std::vector<int64_t> shard_bounds;
+    bool           shard_begun = false;
+    int            pending_ingest_status = 0; // data error of an ingest call between sharded_begin and sharded_finish
 };
+constexpr int    MAX_RANKS = 64;
+// layout of b_coll / h_coll in 8-byte words
+constexpr size_t COLL_SEND = 0;                                       // send staging (<= MAX_RANKS + 8 words)
+constexpr size_t COLL_REC0 = COLL_SEND + MAX_RANKS + 8;               // gathered rec0: nranks x 8 ints (4 words each)
+constexpr size_t COLL_CNT = COLL_REC0 + 4 * MAX_RANKS;                // gathered counts: nranks x (nranks + CNT_EXTRA)
+constexpr int    CNT_EXTRA = 6;                                       // list_n, symmetric, n_rec, status, total_read_len, n_bins
+constexpr size_t COLL_FIN = COLL_CNT + (size_t)MAX_RANKS * (MAX_RANKS + CNT_EXTRA); // gathered finalize words: nranks x 8
+constexpr size_t COLL_OUT = COLL_FIN + 8 * MAX_RANKS;                 // gathered output sizes: nranks x 8
+constexpr size_t COLL_WORDS = COLL_OUT + 8 * MAX_RANKS;
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) {                                                                         \
+            ctx->last_error = std::string(#call) + ": " + ncclGetErrorString(r_);                        \
+            return RAFTGPU_E_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
 constexpr int    OFF_SAMPLE = 256;
 constexpr size_t SEQ_CHUNK = 256ull << 20;
 constexpr int    FRAG_SAMPLE = 256;
@@ -206,6 +239,7 @@ const char* raftgpu_strerror(int s)
     case RAFTGPU_E_ARG: return "bad argument";
     case RAFTGPU_E_UNSUPPORTED: return "not supported";
     case RAFTGPU_E_SIM_NAME: return "simulated-read mode (first name matches read=N,align,position=a-b,length=L,chr) but a later name does not";
+    case RAFTGPU_E_PEER: return "another rank of the sharded run failed";
     default: return "unknown status";
     }
 }
@@ -254,6 +288,8 @@ int raftgpu_destroy(raftgpu_ctx* ctx)
     if (ctx->st_aux) { cudaStreamSynchronize(ctx->st_aux); cudaStreamDestroy(ctx->st_aux); }
     if (ctx->st_h2d) { cudaStreamSynchronize(ctx->st_h2d); cudaStreamDestroy(ctx->st_h2d); }
     for (auto& e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->h_coll) cudaFreeHost(ctx->h_coll);
     cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->st2);
     delete ctx;
     return RAFTGPU_OK;
@@ -266,13 +302,14 @@ int raftgpu_reset(raftgpu_ctx* ctx)
     if (ctx->st_h2d) CK(cudaStreamSynchronize(ctx->st_h2d)); // an upload in flight still reads the caller's host arena
     ctx->seq_host = nullptr; ctx->seq_host_bytes = 0; ctx->seq_upload_started = false; ctx->n_chunks = 0;
     Misc h{};
-    h.err.index = LLONG_MAX; h.err_range.index = LLONG_MAX;
+    h.err.packed = ERR_CLEAN; h.err_range.packed = ERR_CLEAN;
     CK(cudaMemcpyAsync(ctx->b_misc.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
     ctx->have_reads = ctx->have_seq = false; ctx->n = ctx->m = ctx->own_first = 0;
-    ctx->n_rec = 0; ctx->carry.clear(); ctx->first_is_local = true; ctx->rec0_external = ctx->sym_external = false;
+    ctx->n_rec = 0; ctx->carry.clear(); ctx->first_is_local = 1; ctx->rec0_external = ctx->sym_external = false;
     ctx->paf_done = false; ctx->paf_bytes = 0; ctx->diff_zeroed = ctx->finalized = ctx->sized = false;
     ctx->q_scattered = false; ctx->h_sym = 0;
+    ctx->shard_begun = false; ctx->pending_ingest_status = 0; ctx->gather_on = false;
     ctx->fasta_active = false; ctx->fa_n = ctx->fa_bases = ctx->fa_name_bytes = 0; ctx->fa_carry.clear();
     ctx->fa_fastq = false; ctx->fa_lines = ctx->fa_text_bytes = 0; ctx->fa_ends_nl = true; ctx->fa_mode_known = false;
     ctx->sn_len = 0; ctx->sn_G = 0; ctx->sn_bytes = 0;
@@ -290,13 +327,13 @@ static int fetch_err(raftgpu_ctx* ctx)
     ErrState e2[2];
     CK(cudaMemcpyAsync(e2, &ctx->misc()->err, sizeof e2, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    ErrState e = e2[0].index != LLONG_MAX ? e2[0] : e2[1]; // unknown names / duplicates first, then range errors of the fused scatter
-    if (e.index != LLONG_MAX) {
-        ctx->err_index = e.index;
+    ErrState e = e2[0].packed != ERR_CLEAN ? e2[0] : e2[1]; // unknown names / duplicates first, then range errors of the fused scatter
+    if (e.packed != ERR_CLEAN) {
+        ctx->err_index = err_index(e);
         char buf[160];
-        snprintf(buf, sizeof buf, "%s (index %lld)", raftgpu_strerror(e.code), e.index);
+        snprintf(buf, sizeof buf, "%s (index %lld)", raftgpu_strerror(err_code(e)), err_index(e));
         ctx->last_error = buf;
-        return e.code;
+        return err_code(e);
     }
     return RAFTGPU_OK;
 }
@@ -405,7 +442,7 @@ static int build_layout_and_names(raftgpu_ctx* ctx, const std::string& first_nam
         ctx->launches += 3;
         int st = fetch_err(ctx);
         if (st == RAFTK_E_HASH_COLLISION) { // astronomically rare: rebuild with another seed
-            ErrState clean{LLONG_MAX, 0, 0};
+            ErrState clean{ERR_CLEAN, 0};
             CK(cudaMemcpyAsync(&ctx->misc()->err, &clean, sizeof clean, cudaMemcpyHostToDevice, ctx->st));
             continue;
         }
@@ -718,7 +755,7 @@ static int tokenize_device(raftgpu_ctx* ctx, const uint8_t* dtext, int64_t len)
         a.text = dtext; a.nbytes = len; a.rec_base = ctx->n_rec; a.rec_cap = ctx->rec_cap;
         a.qid = ctx->b_qid.as<int32_t>(); a.tid = ctx->b_tid.as<int32_t>(); a.qs = ctx->b_qs.as<int32_t>(); a.qe = ctx->b_qe.as<int32_t>();
         a.ts = ctx->b_ts.as<int32_t>(); a.te = ctx->b_te.as<int32_t>(); a.strand = ctx->b_strand.as<uint8_t>();
-        a.rec0 = M->rec0; a.first_is_local = ctx->first_is_local ? 1 : 0; a.n_tiles = tiles;
+        a.rec0 = M->rec0; a.first_is_local = ctx->first_is_local; a.n_tiles = tiles;
         a.status = ctx->b_status.as<uint64_t>(); a.ticket = &M->ticket; a.sym_flag = &M->sym_flag; a.err = &M->err;
         a.n_records_out = (int64_t*)&M->n_records_out; a.names = ctx->nt;
         // a retry (record capacity overflow) decodes the same lines again: their query sides are already in
@@ -777,7 +814,11 @@ extern "C" int raftgpu_ingest_paf(raftgpu_ctx* ctx, const uint8_t* text, size_t 
         ctx->carry.clear();
     }
     int st = tokenize_device(ctx, dtext, (int64_t)proc);
-    if (st) return st;
+    if (st) {
+        // a sharded run must still reach its collectives: remember the data error for raftgpu_sharded_finish
+        if (ctx->shard_begun && (st == RAFTGPU_E_UNKNOWN_NAME || st == RAFTGPU_E_RANGE)) { ctx->pending_ingest_status = st; ctx->paf_done = true; }
+        return st;
+    }
     if (last_chunk) {
         ctx->paf_done = true;
         if ((st = start_seq_upload(ctx))) return st; // PAF is on the device: the arena upload can overlap everything that follows
@@ -822,7 +863,7 @@ extern "C" int raftgpu_set_first_record(raftgpu_ctx* ctx, const int32_t rec[6], 
     int r[8] = {0};
     if (rec) { for (int k = 0; k < 6; k++) r[k] = rec[k]; r[6] = 1; }
     CK(cudaMemcpy(ctx->misc()->rec0, r, sizeof r, cudaMemcpyHostToDevice));
-    ctx->rec0_external = true; ctx->first_is_local = is_local != 0;
+    ctx->rec0_external = true; ctx->first_is_local = is_local != 0 ? 1 : 0;
     return RAFTGPU_OK;
 }
 extern "C" int raftgpu_get_symmetric(raftgpu_ctx* ctx, int32_t* flag)
@@ -1011,11 +1052,34 @@ extern "C" int raftgpu_finalize(raftgpu_ctx* ctx, raftgpu_stats* out)
     long long G = 0, R = 0, nrec = ctx->n_rec;
     int       S = 0;
     unsigned long long stats2[2];
+    if (ctx->gather_on) { // sharded run: every rank learns every rank's fragment count, statistics and error words in this same synchronisation
+        const long long* src[3] = {(const long long*)(ctx->b_frag_base.as<int64_t>() + m), (const long long*)&M->stats[0], (const long long*)&M->stats[1]};
+        long long*       snd = ctx->b_coll.as<long long>() + COLL_SEND;
+        launch_pack_scalars(src, 3, &M->err, &M->err_range, snd, ctx->st);
+        CKL();
+        NCK(ncclAllGather(snd, ctx->b_coll.as<long long>() + COLL_FIN, 8, ncclInt64, ctx->comm, ctx->st));
+        CK(cudaMemcpyAsync(ctx->h_coll + COLL_FIN, ctx->b_coll.as<long long>() + COLL_FIN, sizeof(long long) * 8 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->st));
+    }
     CK(cudaMemcpyAsync(&G, ctx->b_frag_base.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&R, ctx->b_rep_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&S, &M->sym_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(stats2, M->stats, sizeof stats2, cudaMemcpyDeviceToHost, ctx->st));
-    if ((st = fetch_err(ctx))) return st;
+    st = fetch_err(ctx);
+    if (ctx->gather_on) {
+        const long long* g = ctx->h_coll + COLL_FIN;
+        raftgpu_shard_info& sh = ctx->shard;
+        sh.n_fragments_total = sh.total_cov = sh.total_repeat_len = 0;
+        long long before = 0;
+        for (int r = 0; r < ctx->nranks; r++) {
+            if (!st && ((unsigned long long)g[8 * r + 3] != ERR_CLEAN || (unsigned long long)g[8 * r + 4] != ERR_CLEAN)) st = RAFTGPU_E_PEER;
+            if (r < ctx->rank) before += g[8 * r];
+            sh.n_fragments_total += g[8 * r]; sh.total_cov += g[8 * r + 1]; sh.total_repeat_len += g[8 * r + 2];
+        }
+        if (st == RAFTGPU_E_PEER) ctx->last_error = "another rank reported a data error";
+        ctx->read_num_base = before;
+        sh.first_read_num = before + 1;
+    }
+    if (st) return st;
     ctx->G = G; ctx->n_repeats = R; ctx->finalized = true;
     raftgpu_stats& s = ctx->stats;
     s.n_reads = ctx->n; s.n_records = nrec; s.symmetric = S; s.high_cov = H; s.real_reads = ctx->real_reads;
@@ -1104,6 +1168,16 @@ static int layout_outputs(raftgpu_ctx* ctx)
         CK(cudaMemcpyAsync(ctx->h_bed_line_off.data(), bs.p, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaMemcpyAsync(&bed_bytes, ctx->b_bed_line_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, ctx->st));
     }
+    if (ctx->gather_on) { // file offsets of this rank's slices: all-gather of the four sizes (+ error words), read in the synchronisation below
+        const long long* src[4] = {(const long long*)(ctx->b_cov_tile_off.as<int64_t>() + T), (const long long*)(ctx->b_rep_line_off.as<int64_t>() + m),
+                                   ctx->real_reads ? (const long long*)&M->zero : (const long long*)(ctx->b_bed_line_off.as<int64_t>() + m),
+                                   (const long long*)(ctx->b_frag_off.as<int64_t>() + G)};
+        long long*       snd = ctx->b_coll.as<long long>() + COLL_SEND;
+        launch_pack_scalars(src, 4, &M->err, &M->err_range, snd, ctx->st);
+        CKL();
+        NCK(ncclAllGather(snd, ctx->b_coll.as<long long>() + COLL_OUT, 8, ncclInt64, ctx->comm, ctx->st));
+        CK(cudaMemcpyAsync(ctx->h_coll + COLL_OUT, ctx->b_coll.as<long long>() + COLL_OUT, sizeof(long long) * 8 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->st));
+    }
     CK(cudaMemcpyAsync(ctx->h_cov_tile_off.data(), ctx->b_off_sample.p, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(ctx->h_rep_line_off.data(), ctx->b_off_sample.as<int64_t>() + nc, sizeof(int64_t) * nr, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaMemcpyAsync(&cov_bytes, ctx->b_cov_tile_off.as<int64_t>() + T, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -1111,6 +1185,16 @@ static int layout_outputs(raftgpu_ctx* ctx)
     CK(cudaMemcpyAsync(&fasta_bytes, ctx->b_frag_off.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, ctx->st));
     cudaEventRecord(ctx->ev[7], ctx->st);
     int st = fetch_err(ctx);
+    if (ctx->gather_on) {
+        const long long* g = ctx->h_coll + COLL_OUT;
+        raftgpu_shard_info& sh = ctx->shard;
+        for (int w = 0; w < 4; w++) { sh.stream_base[w] = 0; sh.stream_total[w] = 0; }
+        for (int r = 0; r < ctx->nranks; r++) {
+            if (!st && ((unsigned long long)g[8 * r + 4] != ERR_CLEAN || (unsigned long long)g[8 * r + 5] != ERR_CLEAN)) st = RAFTGPU_E_PEER;
+            for (int w = 0; w < 4; w++) { if (r < ctx->rank) sh.stream_base[w] += (uint64_t)g[8 * r + w]; sh.stream_total[w] += (uint64_t)g[8 * r + w]; }
+        }
+        if (st == RAFTGPU_E_PEER) ctx->last_error = "another rank reported a data error";
+    }
     if (st) return st;
     raftgpu_stats& s = ctx->stats;
     s.out_bytes[RAFTGPU_OUT_COVERAGE] = (uint64_t)cov_bytes;
@@ -1160,6 +1244,287 @@ extern "C" int raftgpu_run(raftgpu_ctx* ctx, raftgpu_stats* out)
     raftgpu_stats& s = ctx->stats;
     s.ms_total = s.ms_tokenize + s.ms_scatter + s.ms_scan + s.ms_repeat_cut + s.ms_layout;
     if (out) *out = s;
+    return RAFTGPU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ sharded run inside the library (NCCL)
+extern "C" int raftgpu_comm_unique_id(uint8_t id[RAFTGPU_COMM_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == RAFTGPU_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id) return RAFTGPU_E_ARG;
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return RAFTGPU_E_CUDA;
+    memcpy(id, &u, sizeof u);
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_comm_init(raftgpu_ctx* ctx, int nranks, int rank, const uint8_t id[RAFTGPU_COMM_ID_BYTES])
+{
+    if (!ctx || !id || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) return RAFTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NCK(ncclCommInitRank(&ctx->comm, nranks, u, rank));
+    ctx->nranks = nranks; ctx->rank = rank;
+    CK(ctx->b_coll.ensure(sizeof(long long) * COLL_WORDS));
+    if (!ctx->h_coll) CK(cudaHostAlloc((void**)&ctx->h_coll, sizeof(long long) * COLL_WORDS, cudaHostAllocDefault));
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_comm_destroy(raftgpu_ctx* ctx)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (ctx->comm) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->st); ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->nranks = 1; ctx->rank = 0;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_partition_reads(const int64_t* lengths, int64_t n, int32_t reso, int nranks, int64_t* bounds)
+{
+    if (!lengths || !bounds || n < 0 || reso < 1 || nranks < 1) return RAFTGPU_E_ARG;
+    // boundary r = first read whose slots start at or after total * r / nranks (slots = bins + 1 per read)
+    long long total = 0;
+    for (int64_t i = 0; i < n; i++) total += (lengths[i] + reso - 1) / reso + 1;
+    bounds[0] = 0;
+    long long acc = 0;
+    int64_t   i = 0;
+    for (int r = 1; r < nranks; r++) {
+        const long long want = total * r / nranks;
+        while (i < n && acc < want) { acc += (lengths[i] + reso - 1) / reso + 1; i++; }
+        bounds[r] = i;
+    }
+    bounds[nranks] = n;
+    return RAFTGPU_OK;
+}
+
+// forget the PAF of this context (records, flags, differences) but keep the reads: used when the first-record peek has to be redone
+static int reset_paf_state(raftgpu_ctx* ctx)
+{
+    Misc* M = ctx->misc();
+    ctx->n_rec = 0; ctx->carry.clear(); ctx->paf_done = false; ctx->paf_bytes = 0; ctx->q_scattered = false; ctx->h_sym = 0;
+    ctx->diff_zeroed = false; ctx->diff_zero_ints = 0; ctx->stats.ms_tokenize = 0; ctx->shard_begun = false;
+    CK(cudaMemsetAsync(&M->sym_flag, 0, sizeof(int), ctx->st));
+    CK(cudaMemsetAsync(&M->n_records_out, 0, sizeof(long long), ctx->st));
+    return RAFTGPU_OK;
+}
+
+// record 0 of the whole file (chop.hpp:171-184 compares every later record with it): every rank peeks the head of its
+// text, the first records are all-gathered and the first rank that has one wins -- all on the stream, the tokenizer reads
+// the result from device memory.  `whole`: the head is the rank's whole text.
+static int sharded_begin_impl(raftgpu_ctx* ctx, const int64_t* bounds, const uint8_t* head_text, size_t head, bool whole)
+{
+    if (!ctx->comm) FAIL(RAFTGPU_E_STATE, "sharded run: raftgpu_comm_init first");
+    if (!ctx->have_reads || ctx->paf_done || ctx->n_rec || ctx->finalized || !ctx->carry.empty()) FAIL(RAFTGPU_E_STATE, "sharded run: set the reads of this run first");
+    const int P = ctx->nranks, R = ctx->rank;
+    if (bounds[R] != ctx->own_first || bounds[R + 1] != ctx->own_first + ctx->m || bounds[0] != 0 || bounds[P] != ctx->n)
+        FAIL(RAFTGPU_E_ARG, "sharded run: bounds do not match the read range given to raftgpu_set_reads_sharded");
+    CK(cudaSetDevice(ctx->device));
+    ctx->shard_bounds.assign(bounds, bounds + P + 1);
+    Misc*      M = ctx->misc();
+    long long* coll = ctx->b_coll.as<long long>();
+    int*       srec = reinterpret_cast<int*>(coll + COLL_SEND);
+    CK(cudaMemsetAsync(srec, 0, sizeof(int) * 8, ctx->st));
+    const uint8_t* dhead = head_text;
+    if (head && !(is_device_ptr(head_text) && ((uintptr_t)head_text & 15) == 0)) {
+        CK(ctx->b_peek.ensure(head + 64));
+        CK(cudaMemcpyAsync(ctx->b_peek.p, head_text, head, cudaMemcpyDefault, ctx->st));
+        dhead = ctx->b_peek.as<uint8_t>();
+    }
+    if (head) { launch_paf_peek(dhead, (int64_t)head, ctx->nt, srec, &M->err, ctx->st, whole ? 1 : 0); CKL(); }
+    else { const int w = 1; CK(cudaMemcpyAsync(srec + 7, &w, sizeof(int), cudaMemcpyHostToDevice, ctx->st)); }
+    int* grec = reinterpret_cast<int*>(coll + COLL_REC0);
+    NCK(ncclAllGather(srec, grec, 8, ncclInt32, ctx->comm, ctx->st));
+    launch_pick_rec0(grec, P, R, M->rec0, ctx->st);
+    CKL();
+    CK(cudaMemcpyAsync(ctx->h_coll + COLL_REC0, grec, sizeof(int) * 8 * (size_t)P, cudaMemcpyDeviceToHost, ctx->st));
+    ctx->rec0_external = true; ctx->first_is_local = -1; ctx->shard_begun = true;
+    return RAFTGPU_OK;
+}
+// Were the peeked heads enough?  Every rank before the first one that found a record must have peeked its whole text
+// (all ranks read the same gathered flags, so all agree).  Valid once the stream has been synchronised after the begin.
+static bool sharded_peek_ok(const raftgpu_ctx* ctx)
+{
+    const int* hrec = reinterpret_cast<const int*>(ctx->h_coll + COLL_REC0);
+    for (int r = 0; r < ctx->nranks; r++) {
+        if (hrec[8 * r + 6]) return true;
+        if (!hrec[8 * r + 7]) return false;
+    }
+    return true;
+}
+static int sharded_finish_impl(raftgpu_ctx* ctx, int ing, raftgpu_stats* out, raftgpu_shard_info* info);
+
+extern "C" int raftgpu_sharded_begin(raftgpu_ctx* ctx, const int64_t* bounds, const uint8_t* head_text, size_t head_bytes, int head_is_whole_text)
+{
+    if (!ctx || !bounds || (!head_text && head_bytes)) return RAFTGPU_E_ARG;
+    ctx->shard = raftgpu_shard_info{};
+    return sharded_begin_impl(ctx, bounds, head_text, head_bytes, head_is_whole_text != 0);
+}
+
+extern "C" int raftgpu_sharded_finish(raftgpu_ctx* ctx, raftgpu_stats* out, raftgpu_shard_info* info)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->shard_begun) FAIL(RAFTGPU_E_STATE, "raftgpu_sharded_finish: raftgpu_sharded_begin first");
+    int ing = ctx->pending_ingest_status;
+    if (!ing && !ctx->paf_done) ing = raftgpu_ingest_paf(ctx, nullptr, 0, 1);
+    if (ing != RAFTGPU_OK && ing != RAFTGPU_E_UNKNOWN_NAME && ing != RAFTGPU_E_RANGE) return ing;
+    CK(cudaStreamSynchronize(ctx->st));
+    if (!sharded_peek_ok(ctx)) FAIL(RAFTGPU_E_UNSUPPORTED, "the first chunk of a rank's PAF text holds no record although later chunks may: use raftgpu_run_sharded");
+    return sharded_finish_impl(ctx, ing, out, info);
+}
+
+extern "C" int raftgpu_run_sharded(raftgpu_ctx* ctx, const int64_t* bounds, const uint8_t* text, size_t nbytes, raftgpu_stats* out,
+                                   raftgpu_shard_info* info)
+{
+    if (!ctx || !bounds || (!text && nbytes)) return RAFTGPU_E_ARG;
+    ctx->shard = raftgpu_shard_info{};
+    // Should a rank before the winner have a record beyond its peeked head (a PAF whose first megabytes hold no record at
+    // all), every rank sees that in the gathered flags and the step is redone with whole-text peeks.
+    size_t peek_cap = 4u << 20;
+    if (const char* e = getenv("RAFT_B200_PEEK_BYTES")) { long long v = atoll(e); if (v > 0) peek_cap = (size_t)v; } // test knob
+    int ing = RAFTGPU_OK;
+    for (int attempt = 0;; attempt++) {
+        const size_t head = attempt == 0 ? std::min(nbytes, peek_cap) : nbytes;
+        int          st = sharded_begin_impl(ctx, bounds, text, head, head == nbytes);
+        if (st) return st;
+        ing = raftgpu_ingest_paf(ctx, text, nbytes, 1); // synchronises the stream: the gathered peeks are on the host now
+        if (ing != RAFTGPU_OK && ing != RAFTGPU_E_UNKNOWN_NAME && ing != RAFTGPU_E_RANGE) return ing; // not a data error: nothing to agree on
+        if (sharded_peek_ok(ctx) || attempt == 1) break;
+        ctx->shard.peek_retries++;
+        if ((st = reset_paf_state(ctx))) return st;
+    }
+    return sharded_finish_impl(ctx, ing, out, info);
+}
+
+static int sharded_finish_impl(raftgpu_ctx* ctx, int ing, raftgpu_stats* out, raftgpu_shard_info* info)
+{
+    const int  P = ctx->nranks, R = ctx->rank;
+    Misc*      M = ctx->misc();
+    long long* coll = ctx->b_coll.as<long long>();
+    const int64_t* bounds = ctx->shard_bounds.data();
+    raftgpu_shard_info& sh = ctx->shard;
+    sh.nranks = P; sh.rank = R;
+    struct GatherGuard { raftgpu_ctx* c; ~GatherGuard() { c->gather_on = false; c->shard_begun = false; } } guard{ctx};
+    ctx->gather_on = true;
+
+    // ---- symmetric flag: OR over the ranks, in place on the device
+    NCK(ncclAllReduce(&M->sym_flag, &M->sym_flag, 1, ncclInt32, ncclMax, ctx->comm, ctx->st));
+    ctx->sym_external = true;
+    cudaEventRecord(ctx->ev[8], ctx->st);
+    // ---- endpoints for reads of other ranks: count (and collect) per destination, all-gather the count rows
+    CK(ctx->b_bounds.ensure(sizeof(int64_t) * (MAX_RANKS + 1)));
+    CK(ctx->b_route_list.ensure(sizeof(int4) * ROUTE_LIST_CAP));
+    CK(cudaMemcpyAsync(ctx->b_bounds.p, bounds, sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(M->route_counts, 0, sizeof(unsigned long long) * 65, ctx->st));
+    unsigned long long cap = ROUTE_LIST_CAP;
+    if (const char* e = getenv("RAFT_B200_ROUTE_CAP")) { long long v = atoll(e); if (v >= 0 && (unsigned long long)v < cap) cap = (unsigned long long)v; }
+    if (ing == RAFTGPU_OK) {
+        launch_route_collect(scatter_args(ctx), P, ctx->b_bounds.as<int64_t>(), M->route_counts, ctx->b_route_list.as<int4>(), &M->route_list_n, cap, ctx->st);
+        CKL();
+    }
+    const int       W = P + CNT_EXTRA;
+    const long long extra[4] = {(long long)ctx->n_rec, (long long)ing, (long long)ctx->total_read_len, (long long)(ctx->n_slots - ctx->m)};
+    launch_pack_counts(M->route_counts, &M->route_list_n, &M->sym_flag, extra, P, coll + COLL_SEND, ctx->st);
+    CKL();
+    NCK(ncclAllGather(coll + COLL_SEND, coll + COLL_CNT, (size_t)W, ncclInt64, ctx->comm, ctx->st));
+    CK(cudaMemcpyAsync(ctx->h_coll + COLL_CNT, coll + COLL_CNT, sizeof(long long) * (size_t)W * P, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    const long long* g = ctx->h_coll + COLL_CNT;
+    int              st = ing;
+    sh.n_records_total = sh.total_read_len = sh.n_bins_total = 0;
+    for (int r = 0; r < P; r++) {
+        if (!st && g[(size_t)r * W + P + 3]) st = RAFTGPU_E_PEER;
+        sh.n_records_total += g[(size_t)r * W + P + 2]; sh.total_read_len += g[(size_t)r * W + P + 4]; sh.n_bins_total += g[(size_t)r * W + P + 5];
+    }
+    if (st == RAFTGPU_E_PEER) ctx->last_error = "another rank reported a data error while reading its part of the PAF";
+    if (st) return st;
+    if (sh.n_records_total > 0x7fffffffll) FAIL(RAFTGPU_E_ARG, "more than 2^31-1 PAF records (the reference counts them in an int, chop.hpp:139)");
+    const int S = (int)g[(size_t)R * W + P + 1];
+    ctx->h_sym = S; sh.symmetric = S;
+    long long soff[MAX_RANKS + 1], roff[MAX_RANKS + 1];
+    soff[0] = roff[0] = 0;
+    for (int r = 0; r < P; r++) { soff[r + 1] = soff[r] + g[(size_t)R * W + r]; roff[r + 1] = roff[r] + g[(size_t)r * W + R]; }
+    sh.endpoints_sent = soff[P]; sh.endpoints_received = roff[P];
+    const long long listed = g[(size_t)R * W + P];
+    // ---- intervals on reads this rank owns go straight into its differences; the others are bucketed by owner and exchanged
+    if ((st = accumulate_local(ctx))) return st;
+    CK(ctx->b_send.ensure(sizeof(int32_t) * 3 * (size_t)(soff[P] + 1))); CK(ctx->b_recv.ensure(sizeof(int32_t) * 3 * (size_t)(roff[P] + 1)));
+    if (soff[P] > 0) {
+        unsigned long long cur[64] = {0};
+        for (int r = 0; r < P; r++) cur[r] = (unsigned long long)soff[r];
+        CK(cudaMemcpyAsync(M->route_counts, cur, sizeof cur, cudaMemcpyHostToDevice, ctx->st));
+        if ((unsigned long long)listed <= cap) launch_route_pack_list(ctx->b_route_list.as<int4>(), listed, M->route_counts, ctx->b_send.as<int32_t>(), ctx->st);
+        else launch_route_pack(scatter_args(ctx), P, ctx->b_bounds.as<int64_t>(), M->route_counts, ctx->b_send.as<int32_t>(), ctx->st);
+        CKL();
+    }
+    NCK(ncclGroupStart());
+    for (int r = 0; r < P; r++) {
+        if (r == R) continue;
+        const long long ns = soff[r + 1] - soff[r], nr = roff[r + 1] - roff[r];
+        if (ns) NCK(ncclSend(ctx->b_send.as<int32_t>() + 3 * soff[r], (size_t)(3 * ns), ncclInt32, r, ctx->comm, ctx->st));
+        if (nr) NCK(ncclRecv(ctx->b_recv.as<int32_t>() + 3 * roff[r], (size_t)(3 * nr), ncclInt32, r, ctx->comm, ctx->st));
+    }
+    NCK(ncclGroupEnd());
+    if (roff[P] > 0) {
+        if ((st = zero_diff(ctx))) return st;
+        launch_scatter_endpoints(ctx->b_recv.as<int32_t>(), roff[P], ctx->b_slot_off.as<int64_t>(), ctx->b_diff.as<int32_t>(), ctx->prm.reso, ctx->own_first,
+                                 ctx->m, &M->err, ctx->st);
+        CKL();
+    }
+    cudaEventRecord(ctx->ev[9], ctx->st);
+    // ---- local coverage / repeats / cut points; global numbering and file offsets ride on the synchronisations of these two
+    if ((st = raftgpu_finalize(ctx, nullptr))) return st;
+    if ((st = layout_outputs(ctx))) return st;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]) == cudaSuccess) sh.ms_exchange = ms;
+    raftgpu_stats& s = ctx->stats;
+    s.ms_scatter = ms;
+    s.ms_total = s.ms_tokenize + s.ms_scatter + s.ms_scan + s.ms_repeat_cut + s.ms_layout;
+    if (out) *out = s;
+    if (info) *info = sh;
+    return RAFTGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ read tables of a context
+extern "C" int raftgpu_reads_info(raftgpu_ctx* ctx, int64_t* n_local, int64_t* name_bytes, int64_t* seq_bytes)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "raftgpu_reads_info: no reads");
+    CK(cudaSetDevice(ctx->device));
+    int64_t no[2] = {0, 0};
+    CK(cudaMemcpy(&no[0], ctx->d_name_off + ctx->own_first, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&no[1], ctx->d_name_off + ctx->own_first + ctx->m, 8, cudaMemcpyDeviceToHost));
+    if (n_local) *n_local = ctx->m;
+    if (name_bytes) *name_bytes = no[1] - no[0];
+    if (seq_bytes) *seq_bytes = ctx->total_read_len;
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_reads_copy(raftgpu_ctx* ctx, int64_t* name_off, uint8_t* names, int64_t* lengths)
+{
+    if (!ctx) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads) FAIL(RAFTGPU_E_STATE, "raftgpu_reads_copy: no reads");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->st));
+    const int64_t m = ctx->m;
+    std::vector<int64_t> no((size_t)m + 1);
+    CK(cudaMemcpy(no.data(), ctx->d_name_off + ctx->own_first, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost));
+    if (names && no[m] > no[0]) CK(cudaMemcpy(names, ctx->d_names + no[0], (size_t)(no[m] - no[0]), cudaMemcpyDeviceToHost));
+    if (name_off) for (int64_t i = 0; i <= m; i++) name_off[i] = no[i] - no[0];
+    if (lengths) {
+        std::vector<int64_t> so((size_t)m + 1);
+        CK(cudaMemcpy(so.data(), ctx->d_seq_off, sizeof(int64_t) * (size_t)(m + 1), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < m; i++) lengths[i] = so[i + 1] - so[i];
+    }
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_reads_device(raftgpu_ctx* ctx, const int64_t** seq_off, const uint8_t** seq)
+{
+    if (!ctx || !seq_off || !seq) return RAFTGPU_E_ARG;
+    if (!ctx->have_reads || !ctx->have_seq) FAIL(RAFTGPU_E_STATE, "raftgpu_reads_device: no reads with sequence bytes");
+    *seq_off = ctx->d_seq_off; *seq = ctx->d_seq;
     return RAFTGPU_OK;
 }
 
@@ -1394,7 +1759,9 @@ extern "C" int raftgpu_sync(raftgpu_ctx* ctx)
     return fetch_err(ctx);
 }
 
-extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest)
+extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest) { return raftgpu_digest_at(ctx, which, 0, digest); }
+
+extern "C" int raftgpu_digest_at(raftgpu_ctx* ctx, int which, uint64_t stream_base, uint64_t* digest)
 {
     if (!ctx || !digest || which < 0 || which > 4) return RAFTGPU_E_ARG;
     uint64_t total = 0;
@@ -1409,7 +1776,7 @@ extern "C" int raftgpu_digest(raftgpu_ctx* ctx, int which, uint64_t* digest)
     for (uint64_t off = 0; off < total; off += W) {
         size_t len = (size_t)std::min<uint64_t>(W, total - off);
         if ((st = emit_window(ctx, which, (int64_t)off, (int64_t)(off + len), ctx->b_stage[0].as<uint8_t>()))) return st;
-        launch_digest(ctx->b_stage[0].as<uint8_t>(), (int64_t)len, (int64_t)off, &ctx->misc()->digest, ls);
+        launch_digest(ctx->b_stage[0].as<uint8_t>(), (int64_t)len, (int64_t)(stream_base + off), &ctx->misc()->digest, ls);
         CKL();
     }
     unsigned long long d = 0;

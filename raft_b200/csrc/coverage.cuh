@@ -4,12 +4,6 @@
 
 namespace raftk {
 
-__device__ __forceinline__ void err_min(ErrState* err, int code, long long index)
-{
-    long long old = atomicMin(&err->index, index);
-    if (index <= old) err->code = code;
-}
-
 // Adds interval [s,e) of owned local read lr: +1 at its first bin, -1 one past its last bin (repeat.hpp:62-77:
 // lo = max(s,0)/reso, bins lo..(e-1)/reso when e-1 >= lo*reso).  Returns false when it would leave the read's bins
 // (the reference writes out of bounds there).

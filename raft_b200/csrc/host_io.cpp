@@ -2,9 +2,13 @@
 // break_long_reads (chop.hpp:331-373).  No compute here: everything numeric happens on the device
 // through the C ABI in include/raft_b200.h.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -142,24 +146,63 @@ T* steal(const std::vector<T>& v)
     return p;
 }
 
-// Sequential byte source over several files (gzip or plain), read by a background thread into two pinned buffers.
-class FilePipeline {
-public:
-    FilePipeline(const char* const* paths, int n) : paths_(paths, paths + n)
+// Two pinned host buffers shared by every file phase of a run (reads in, PAF in, outputs out): pinning is the expensive
+// part of a small run, so it is done once and sized by the largest file at hand.
+struct PinnedPair {
+    uint8_t* buf[2] = {nullptr, nullptr};
+    bool     pinned[2] = {false, false};
+    size_t   cap = 0;
+    explicit PinnedPair(size_t want)
     {
+        cap = std::min<size_t>(256u << 20, std::max<size_t>(want, 1u << 20));
+        cap = (cap + 4095) & ~(size_t)4095;
         for (int k = 0; k < 2; k++) {
             void* p = nullptr;
-            if (cudaHostAlloc(&p, CAP, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = malloc(CAP); pinned_[k] = false; }
-            buf_[k] = (uint8_t*)p;
+            if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) == cudaSuccess) pinned[k] = true;
+            else { cudaGetLastError(); p = malloc(cap); }
+            buf[k] = (uint8_t*)p;
         }
+    }
+    ~PinnedPair()
+    {
+        for (int k = 0; k < 2; k++) if (buf[k]) { if (pinned[k]) cudaFreeHost(buf[k]); else free(buf[k]); }
+    }
+    bool ok() const { return buf[0] && buf[1]; }
+};
+
+// One piece of input: bytes [off, off+len) of a plain file (len < 0: to the end), or a whole gzip file.
+struct Segment { std::string path; int64_t off = 0, len = -1; bool gz = false; };
+
+bool is_gzip_file(const char* path)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    unsigned char m[2] = {0, 0};
+    const size_t  got = fread(m, 1, 2, f);
+    fclose(f);
+    return got == 2 && m[0] == 0x1f && m[1] == 0x8b;
+}
+int64_t file_size(const char* path)
+{
+    struct stat sb;
+    return stat(path, &sb) == 0 ? (int64_t)sb.st_size : -1;
+}
+
+// Sequential byte source over a list of segments, read by a background thread into the two pinned buffers: plain files
+// with pread straight into pinned memory, gzip files through zlib (paf.hpp:24-38, chop.hpp:93).  With `join_lines` a
+// newline is inserted between two segments when the first does not end with one, so that the last line of one file is
+// never glued to the first line of the next.
+class ByteSource {
+public:
+    ByteSource(PinnedPair& pp, std::vector<Segment> segs, bool join_lines) : pp_(pp), segs_(std::move(segs)), join_(join_lines)
+    {
         th_ = std::thread([this] { run(); });
     }
-    ~FilePipeline()
+    ~ByteSource()
     {
         { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
         cv_.notify_all();
         if (th_.joinable()) th_.join();
-        for (int k = 0; k < 2; k++) if (buf_[k]) { if (pinned_[k]) cudaFreeHost(buf_[k]); else free(buf_[k]); }
     }
     // next filled buffer; false on a read error
     bool next(const uint8_t** data, size_t* fill, bool* last)
@@ -167,7 +210,7 @@ public:
         std::unique_lock<std::mutex> g(mu_);
         cv_.wait(g, [&] { return state_[cons_] == FULL || error_; });
         if (error_) return false;
-        *data = buf_[cons_]; *fill = fill_[cons_]; *last = last_[cons_];
+        *data = pp_.buf[cons_]; *fill = fill_[cons_]; *last = last_[cons_];
         return true;
     }
     void release()
@@ -177,14 +220,17 @@ public:
     }
 
 private:
-    static constexpr size_t CAP = 256u << 20;
     enum { EMPTY, FULL };
     void run()
     {
-        size_t file = 0;
-        gzFile gz = nullptr;
-        int    k = 0;
-        bool   done = false;
+        size_t  seg = 0;
+        gzFile  gz = nullptr;
+        int     fd = -1;
+        int64_t pos = 0, end = 0;
+        int     k = 0;
+        bool    done = false, open = false;
+        uint8_t last_byte = '\n';
+        const size_t CAP = pp_.cap;
         while (!done) {
             {
                 std::unique_lock<std::mutex> g(mu_);
@@ -193,16 +239,35 @@ private:
             }
             size_t fill = 0;
             while (fill < CAP && !done) {
-                if (!gz) {
-                    if (file == paths_.size()) { done = true; break; }
-                    gz = gzopen(paths_[file++], "r"); // transparent for plain files, like the reference (paf.hpp:29)
-                    if (!gz) { fail(); return; }
-                    gzbuffer(gz, 4 << 20);
+                if (!open) {
+                    if (seg == segs_.size()) { done = true; break; }
+                    if (join_ && seg > 0 && last_byte != '\n') { pp_.buf[k][fill++] = '\n'; last_byte = '\n'; continue; }
+                    const Segment& sg = segs_[seg++];
+                    if (sg.gz) {
+                        gz = gzopen(sg.path.c_str(), "r");
+                        if (!gz) { fail(); return; }
+                        gzbuffer(gz, 4 << 20);
+                    } else {
+                        fd = ::open(sg.path.c_str(), O_RDONLY);
+                        if (fd < 0) { fail(); return; }
+                        pos = sg.off;
+                        end = sg.len < 0 ? INT64_MAX : sg.off + sg.len;
+                    }
+                    open = true;
+                    continue;
                 }
-                int got = gzread(gz, buf_[k] + fill, (unsigned)std::min<size_t>(CAP - fill, 1u << 30));
-                if (got < 0) { gzclose(gz); fail(); return; }
-                if (got == 0) { gzclose(gz); gz = nullptr; continue; }
+                long got;
+                if (gz) {
+                    got = gzread(gz, pp_.buf[k] + fill, (unsigned)std::min<size_t>(CAP - fill, 1u << 30));
+                } else {
+                    const size_t want = (size_t)std::min<int64_t>((int64_t)(CAP - fill), end - pos);
+                    got = want ? (long)pread(fd, pp_.buf[k] + fill, want, (off_t)pos) : 0;
+                    if (got > 0) pos += got;
+                }
+                if (got < 0) { close_cur(gz, fd); fail(); return; }
+                if (got == 0) { close_cur(gz, fd); open = false; continue; }
                 fill += (size_t)got;
+                last_byte = pp_.buf[k][fill - 1];
             }
             {
                 std::lock_guard<std::mutex> g(mu_);
@@ -211,24 +276,29 @@ private:
             cv_.notify_all();
             k ^= 1;
         }
-        if (gz) gzclose(gz);
+        close_cur(gz, fd);
+    }
+    static void close_cur(gzFile& gz, int& fd)
+    {
+        if (gz) { gzclose(gz); gz = nullptr; }
+        if (fd >= 0) { ::close(fd); fd = -1; }
     }
     void fail()
     {
         { std::lock_guard<std::mutex> g(mu_); error_ = true; }
         cv_.notify_all();
     }
-    std::vector<const char*> paths_;
-    uint8_t*                 buf_[2] = {nullptr, nullptr};
-    bool                     pinned_[2] = {true, true};
-    size_t                   fill_[2] = {0, 0};
-    bool                     last_[2] = {false, false};
-    int                      state_[2] = {EMPTY, EMPTY};
-    int                      cons_ = 0;
-    bool                     stop_ = false, error_ = false;
-    std::mutex               mu_;
-    std::condition_variable  cv_;
-    std::thread              th_;
+    PinnedPair&          pp_;
+    std::vector<Segment> segs_;
+    bool                 join_;
+    size_t               fill_[2] = {0, 0};
+    bool                 last_[2] = {false, false};
+    int                  state_[2] = {EMPTY, EMPTY};
+    int                  cons_ = 0;
+    bool                 stop_ = false, error_ = false;
+    std::mutex           mu_;
+    std::condition_variable cv_;
+    std::thread          th_;
 };
 
 bool file_missing_or_empty(const char* fn)
@@ -263,25 +333,18 @@ extern "C" int raftgpu_load_fasta(const char* path, int64_t* n, int64_t** seq_of
     return RAFTGPU_OK;
 }
 
-// Writes one output stream to `path`: this thread fetches 256 MiB windows into two pinned buffers (D2H through the
-// C ABI) while a writer thread drains the other buffer to the file.
-static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, std::string& err)
+// Writes the context's slice of one output stream at `file_base` of the open file: this thread fetches windows into the
+// two pinned buffers (D2H through the C ABI) while a writer thread drains the other buffer with pwrite.
+static bool write_stream(raftgpu_ctx* ctx, int which, int fd, uint64_t file_base, PinnedPair& pp, std::string& err)
 {
     uint64_t total = 0;
     if (raftgpu_output_size(ctx, which, &total)) { err = raftgpu_last_error(ctx); return false; }
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) { err = "cannot open " + path; return false; }
-    const size_t W = (size_t)std::min<uint64_t>(256u << 20, total ? total : 1);
-    uint8_t*     buf[2] = {nullptr, nullptr};
-    bool         pinned[2] = {true, true};
-    for (int k = 0; k < 2; k++) {
-        void* p = nullptr;
-        if (cudaHostAlloc(&p, W, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); p = malloc(W); pinned[k] = false; }
-        buf[k] = (uint8_t*)p;
-    }
+    if (!total) return true;
+    const size_t            W = pp.cap;
     std::mutex              mu;
     std::condition_variable cv;
     size_t                  len[2] = {0, 0};
+    uint64_t                at[2] = {0, 0};
     bool                    full[2] = {false, false}, done = false, werr = false;
     std::thread writer([&] {
         for (int k = 0;; k ^= 1) {
@@ -289,7 +352,11 @@ static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, s
             cv.wait(g, [&] { return full[k] || done; });
             if (!full[k]) return;
             g.unlock();
-            if (!werr && fwrite(buf[k], 1, len[k], f) != len[k]) werr = true;
+            size_t put = 0;
+            while (!werr && put < len[k]) {
+                ssize_t w = pwrite(fd, pp.buf[k] + put, len[k] - put, (off_t)(at[k] + put));
+                if (w <= 0) werr = true; else put += (size_t)w;
+            }
             g.lock();
             full[k] = false;
             cv.notify_all();
@@ -303,11 +370,11 @@ static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, s
             cv.wait(g, [&] { return !full[k]; });
         }
         const size_t n = (size_t)std::min<uint64_t>(W, total - off);
-        const int    st = raftgpu_fetch(ctx, which, off, buf[k], n);
+        const int    st = raftgpu_fetch(ctx, which, off, pp.buf[k], n);
         if (st) { err = std::string(raftgpu_strerror(st)) + ": " + raftgpu_last_error(ctx); ok = false; break; }
         {
             std::lock_guard<std::mutex> g(mu);
-            len[k] = n; full[k] = true;
+            len[k] = n; at[k] = file_base + off; full[k] = true;
         }
         cv.notify_all();
     }
@@ -318,10 +385,54 @@ static bool write_stream(raftgpu_ctx* ctx, int which, const std::string& path, s
     }
     cv.notify_all();
     writer.join();
-    for (int q = 0; q < 2; q++) if (buf[q]) { if (pinned[q]) cudaFreeHost(buf[q]); else free(buf[q]); }
-    if (fclose(f) != 0) werr = true;
-    if (werr && ok) { err = "short write to " + path; ok = false; }
+    if (werr && ok) { err = "short write"; ok = false; }
     return ok;
+}
+
+static const char* const OUT_SUFFIX[4] = {".coverage.txt", ".long_repeats.txt", ".long_repeats.bed", ".reads.fasta"};
+
+static void print_run_lines(const raftgpu_params* p, int real_reads, int symmetric, long long n_records, int high_cov, long long total_cov,
+                            long long n_bins, long long total_repeat_len, long long total_read_len)
+{
+    const int total_windows = (int)(uint32_t)(uint64_t)n_bins;           // an int in the reference (repeat.hpp:95,117): wraps past 2^31
+    printf("Real Reads %d \n", real_reads);                              // chop.hpp:105
+    printf("INFO, Symmetric overlaps %d \n", symmetric);                 // chop.hpp:189
+    printf("INFO, length of alignments  %d()\n", (int)n_records);        // chop.hpp:190
+    printf("high_cov %d\n", high_cov);                                   // repeat.hpp:91
+    double coverage_per_window = (double)total_cov / total_windows;      // repeat.hpp:173-178
+    double fraction_of_repeat_length = (double)total_repeat_len / total_read_len;
+    printf("coverage per window is %f \n", coverage_per_window);
+    printf("coverage per window/average coverage is %f \n", coverage_per_window / p->est_cov);
+    printf("fraction_of_repeat_length %f \n", fraction_of_repeat_length);
+}
+
+struct Timer {
+    bool on = getenv("RAFT_B200_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what, int rank = -1)
+    {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[raft_b200 timing] %s%s%s %.3f s\n", what, rank >= 0 ? " rank " : "", rank >= 0 ? std::to_string(rank).c_str() : "",
+                std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+
+// plain FASTA text on the device (K0); RAFTGPU_E_UNSUPPORTED when the text needs the host reader
+static int ingest_fasta_segments(raftgpu_ctx* ctx, PinnedPair& pp, const std::vector<Segment>& segs, uint64_t total_hint)
+{
+    ByteSource src(pp, segs, false);
+    for (;;) {
+        const uint8_t* data = nullptr;
+        size_t         fill = 0;
+        bool           last = false;
+        if (!src.next(&data, &fill, &last)) return RAFTGPU_E_IO;
+        const int st = raftgpu_ingest_fasta(ctx, data, fill, last ? 1 : 0, total_hint);
+        src.release();
+        if (st) return st;
+        if (last) return RAFTGPU_OK;
+    }
 }
 
 extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* paffilename, const raftgpu_params* p, const char* prefix,
@@ -330,12 +441,8 @@ extern "C" int raftgpu_break_long_reads(const char* readfilename, const char* pa
     return raftgpu_break_long_reads_multi(readfilename, 1, &paffilename, p, prefix, device, stats_out);
 }
 
-extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_paf, const char* const* paffilenames, const raftgpu_params* p,
-                                              const char* prefix, int device, raftgpu_stats* stats_out)
+static int validate_inputs(const char* readfilename, int n_paf, const char* const* paffilenames, const std::string& pre)
 {
-    if (!readfilename || n_paf < 1 || !paffilenames || !p || !prefix) return RAFTGPU_E_ARG;
-    for (int k = 0; k < n_paf; k++) if (!paffilenames[k]) return RAFTGPU_E_ARG;
-    const std::string pre(prefix);
     { std::ofstream touch(pre + ".reads.fasta"); } // chop.hpp:333: created before the inputs are validated
     if (file_missing_or_empty(readfilename)) {
         printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", readfilename);
@@ -346,40 +453,38 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
             printf("ERROR, break_long_reads(), %s input file either does not exist or is empty\n", paffilenames[k]);
             return RAFTGPU_E_IO;
         }
+    return RAFTGPU_OK;
+}
+
+extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_paf, const char* const* paffilenames, const raftgpu_params* p,
+                                              const char* prefix, int device, raftgpu_stats* stats_out)
+{
+    if (!readfilename || n_paf < 1 || !paffilenames || !p || !prefix) return RAFTGPU_E_ARG;
+    for (int k = 0; k < n_paf; k++) if (!paffilenames[k]) return RAFTGPU_E_ARG;
+    const std::string pre(prefix);
+    int st = validate_inputs(readfilename, n_paf, paffilenames, pre);
+    if (st) return st;
+    Timer tm;
     raftgpu_ctx* ctx = nullptr;
-    int          st = raftgpu_create(p, device, &ctx);
+    st = raftgpu_create(p, device, &ctx);
     if (st) { fprintf(stderr, "raft_b200: %s\n", raftgpu_strerror(st)); return st; }
     auto fail = [&](int code) {
         fprintf(stderr, "raft_b200: %s: %s\n", raftgpu_strerror(code), raftgpu_last_error(ctx));
         raftgpu_destroy(ctx);
         return code;
     };
+    int64_t biggest = file_size(readfilename);
+    for (int k = 0; k < n_paf; k++) biggest = std::max(biggest, file_size(paffilenames[k]));
+    PinnedPair pp((size_t)std::max<int64_t>(biggest, 0));
+    if (!pp.ok()) return fail(RAFTGPU_E_NOMEM);
+    tm.lap("context + pinned buffers");
 
-    // reads: plain FASTA text is tokenised on the device; gzip, FASTQ and CR LF text go through the host reader
+    // reads: plain FASTA text is tokenised on the device; gzip, wrapped FASTQ and CR LF text go through the host reader
     bool on_device = false;
-    {
-        FILE* f = fopen(readfilename, "rb");
-        if (!f) return fail(RAFTGPU_E_IO);
-        unsigned char magic[2] = {0, 0};
-        size_t        got = fread(magic, 1, 2, f);
-        if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
-            fseeko(f, 0, SEEK_END);
-            const uint64_t fsize = (uint64_t)ftello(f);
-            FilePipeline   pipe(&readfilename, 1); // reader thread + two pinned buffers, like the PAF below
-            st = RAFTGPU_OK;
-            while (st == RAFTGPU_OK) {
-                const uint8_t* data = nullptr;
-                size_t         fill = 0;
-                bool           last = false;
-                if (!pipe.next(&data, &fill, &last)) { fclose(f); return fail(RAFTGPU_E_IO); }
-                st = raftgpu_ingest_fasta(ctx, data, fill, last ? 1 : 0, fsize);
-                pipe.release();
-                if (last) break;
-            }
-            if (st == RAFTGPU_OK) on_device = true;
-            else if (st != RAFTGPU_E_UNSUPPORTED) { fclose(f); return fail(st); }
-        }
-        fclose(f);
+    if (!is_gzip_file(readfilename)) {
+        st = ingest_fasta_segments(ctx, pp, {Segment{readfilename, 0, -1, false}}, (uint64_t)std::max<int64_t>(file_size(readfilename), 0));
+        if (st == RAFTGPU_OK) on_device = true;
+        else if (st != RAFTGPU_E_UNSUPPORTED) return fail(st);
     }
     raftgpu_stats s{};
     if (!on_device) {
@@ -391,43 +496,290 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
         free(seq_off); free(seq); free(name_off); free(names);
         if (st) return fail(st);
     }
+    tm.lap("reads");
 
-    // PAF: one reader thread inflates (gz, paf.hpp:24-38) or reads (plain) the files back to back into two pinned
+    // PAF: one reader thread inflates (gz, paf.hpp:24-38) or reads (plain) the files back to back into the two pinned
     // buffers while this thread hands the other buffer to the tokenizer, so disk/zlib time overlaps H2D + parse and
-    // only the decoded records (28 B each) stay on the device: the text itself may exceed HBM.  Several files behave
+    // only the decoded records (25 B each) stay on the device: the text itself may exceed HBM.  Several files behave
     // like `cat a b | raft ...` (README.md:32-38: hifiasm writes two *.ovlp.paf files).
     {
-        FilePipeline pipe(paffilenames, n_paf);
+        std::vector<Segment> segs;
+        for (int k = 0; k < n_paf; k++) segs.push_back(Segment{paffilenames[k], 0, -1, is_gzip_file(paffilenames[k])});
+        ByteSource src(pp, segs, true);
         for (;;) {
             const uint8_t* data = nullptr;
             size_t         fill = 0;
             bool           last = false;
-            if (!pipe.next(&data, &fill, &last)) return fail(RAFTGPU_E_IO);
+            if (!src.next(&data, &fill, &last)) return fail(RAFTGPU_E_IO);
             st = raftgpu_ingest_paf(ctx, data, fill, last ? 1 : 0);
-            pipe.release();
+            src.release();
             if (st) return fail(st);
             if (last) break;
         }
     }
-    if ((st = raftgpu_run(ctx, &s))) {
-        // the reference prints these before it would have crashed; keep stdout comparable up to the failure
-        return fail(st);
-    }
-    printf("Real Reads %d \n", s.real_reads);                              // chop.hpp:105
-    printf("INFO, Symmetric overlaps %d \n", s.symmetric);                 // chop.hpp:189
-    printf("INFO, length of alignments  %d()\n", (int)s.n_records);        // chop.hpp:190
-    printf("high_cov %d\n", s.high_cov);                                   // repeat.hpp:91
-    double coverage_per_window = (double)s.total_cov / s.total_windows;    // repeat.hpp:173-178
-    double fraction_of_repeat_length = (double)s.total_repeat_len / s.total_read_len;
-    printf("coverage per window is %f \n", coverage_per_window);
-    printf("coverage per window/average coverage is %f \n", coverage_per_window / p->est_cov);
-    printf("fraction_of_repeat_length %f \n", fraction_of_repeat_length);
+    tm.lap("paf");
+    if ((st = raftgpu_run(ctx, &s))) return fail(st);
+    tm.lap("run");
+    print_run_lines(p, s.real_reads, s.symmetric, s.n_records, s.high_cov, s.total_cov, s.n_bins, s.total_repeat_len, s.total_read_len);
 
     std::string err;
-    const char* suf[4] = {".coverage.txt", ".long_repeats.txt", ".long_repeats.bed", ".reads.fasta"};
-    for (int w = 0; w < 4; w++)
-        if (!write_stream(ctx, w, pre + suf[w], err)) { fprintf(stderr, "raft_b200: %s\n", err.c_str()); raftgpu_destroy(ctx); return RAFTGPU_E_IO; }
+    for (int w = 0; w < 4; w++) {
+        const std::string path = pre + OUT_SUFFIX[w];
+        int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        bool ok = fd >= 0 && write_stream(ctx, w, fd, 0, pp, err);
+        if (fd >= 0 && ::close(fd) != 0) ok = false;
+        if (!ok) { fprintf(stderr, "raft_b200: cannot write %s: %s\n", path.c_str(), err.c_str()); raftgpu_destroy(ctx); return RAFTGPU_E_IO; }
+        tm.lap(OUT_SUFFIX[w]);
+    }
     if (stats_out) *stats_out = s;
     raftgpu_destroy(ctx);
+    tm.lap("destroy");
+    return RAFTGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ several GPUs of one box
+namespace {
+
+struct Barrier { // reusable; wait() returns the OR of the flags passed by the threads of this round
+    explicit Barrier(int n) : n_(n) {}
+    bool wait(bool flag = false)
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        acc_ = acc_ || flag;
+        const int gen = gen_;
+        if (++count_ == n_) { result_ = acc_; acc_ = false; count_ = 0; gen_++; cv_.notify_all(); return result_; }
+        cv_.wait(g, [&] { return gen_ != gen; });
+        return result_;
+    }
+    int n_, count_ = 0, gen_ = 0;
+    bool acc_ = false, result_ = false;
+    std::mutex mu_;
+    std::condition_variable cv_;
+};
+
+// first byte after the first '\n' at or after `pos` whose next byte satisfies `starts_record` (any byte when null); file size when none
+int64_t next_line_start(int fd, int64_t pos, int64_t size, bool want_gt)
+{
+    std::vector<uint8_t> buf(1 << 20);
+    if (pos <= 0) return 0;
+    int64_t at = pos - 1; // a record may start exactly at pos: look at the byte before it
+    bool    prev_nl = false;
+    while (at < size) {
+        const ssize_t got = pread(fd, buf.data(), buf.size(), (off_t)at);
+        if (got <= 0) break;
+        for (ssize_t i = 0; i < got; i++) {
+            if (prev_nl && (!want_gt || buf[i] == '>')) return at + i;
+            prev_nl = buf[i] == '\n';
+        }
+        at += got;
+    }
+    return size;
+}
+
+struct MgpuShared {
+    int                  P = 0;
+    std::vector<int>     devices;
+    std::vector<raftgpu_ctx*> ctx;
+    uint8_t              comm_id[RAFTGPU_COMM_ID_BYTES];
+    std::vector<int>     status;
+    // reads
+    bool                 device_reads = false;
+    std::vector<Segment> fasta_seg;
+    std::vector<int64_t> n_local, name_bytes;
+    std::vector<int64_t> bounds, name_base;
+    std::vector<int64_t> lengths_all, name_off_all;
+    std::vector<uint8_t> names_all;
+    int64_t              hn = 0;
+    int64_t *            hseq_off = nullptr, *hname_off = nullptr;
+    uint8_t *            hseq = nullptr, *hnames = nullptr;
+    // PAF
+    std::vector<std::vector<Segment>> paf_seg;
+    // results
+    std::vector<raftgpu_shard_info> info;
+    std::vector<raftgpu_stats>      stats;
+    int                  out_fd[4] = {-1, -1, -1, -1};
+    std::string          err;
+    std::mutex           mu;
+};
+
+} // namespace
+
+extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf, const char* const* paffilenames, const raftgpu_params* p,
+                                             const char* prefix, int ndev, const int* devices, raftgpu_stats* stats_out)
+{
+    if (!readfilename || n_paf < 1 || !paffilenames || !p || !prefix || ndev < 1 || ndev > 64 || !devices) return RAFTGPU_E_ARG;
+    if (ndev == 1) return raftgpu_break_long_reads_multi(readfilename, n_paf, paffilenames, p, prefix, devices[0], stats_out);
+    for (int k = 0; k < n_paf; k++) if (!paffilenames[k]) return RAFTGPU_E_ARG;
+    const std::string pre(prefix);
+    int st = validate_inputs(readfilename, n_paf, paffilenames, pre);
+    if (st) return st;
+    Timer      tm;
+    MgpuShared sh;
+    const int  P = ndev;
+    sh.P = P; sh.devices.assign(devices, devices + P);
+    sh.ctx.assign(P, nullptr); sh.status.assign(P, 0); sh.n_local.assign(P, 0); sh.name_bytes.assign(P, 0);
+    sh.info.assign(P, raftgpu_shard_info{}); sh.stats.assign(P, raftgpu_stats{}); sh.paf_seg.assign(P, {});
+    auto destroy_all = [&] { for (auto& c : sh.ctx) if (c) { raftgpu_destroy(c); c = nullptr; } };
+    for (int r = 0; r < P; r++)
+        if ((st = raftgpu_create(p, devices[r], &sh.ctx[r]))) { fprintf(stderr, "raft_b200: device %d: %s\n", devices[r], raftgpu_strerror(st)); destroy_all(); return st; }
+    if ((st = raftgpu_comm_unique_id(sh.comm_id))) { destroy_all(); return st; }
+
+    // ---- how the inputs are cut.  Reads: plain FASTA is cut into P byte ranges at record starts ('>' opening a line), each
+    // tokenised on its own GPU, and that cut IS the read partition (bytes ~ bases ~ coverage slots); anything else (gzip,
+    // FASTQ, CR LF) is read once by the host reader and partitioned by coverage slots.  PAF: every plain file is cut
+    // into P byte ranges at line ends; a gzip file cannot be cut and goes to one rank as a whole.
+    const int64_t fsize = file_size(readfilename);
+    {
+        int fd = ::open(readfilename, O_RDONLY);
+        uint8_t first = 0;
+        if (fd >= 0 && !is_gzip_file(readfilename) && pread(fd, &first, 1, 0) == 1 && first == '>') {
+            sh.device_reads = true;
+            std::vector<int64_t> cut(P + 1, fsize);
+            cut[0] = 0;
+            for (int r = 1; r < P; r++) cut[r] = std::max(cut[r - 1], next_line_start(fd, fsize / P * r, fsize, true));
+            for (int r = 0; r < P; r++) sh.fasta_seg.push_back(Segment{readfilename, cut[r], cut[r + 1] - cut[r], false});
+        }
+        if (fd >= 0) ::close(fd);
+    }
+    int64_t biggest = sh.device_reads ? fsize / P + 1 : 0;
+    for (int k = 0; k < n_paf; k++) {
+        const int64_t sz = file_size(paffilenames[k]);
+        if (is_gzip_file(paffilenames[k])) { sh.paf_seg[k % P].push_back(Segment{paffilenames[k], 0, -1, true}); biggest = std::max<int64_t>(biggest, 64 << 20); continue; }
+        int fd = ::open(paffilenames[k], O_RDONLY);
+        if (fd < 0) { destroy_all(); return RAFTGPU_E_IO; }
+        std::vector<int64_t> cut(P + 1, sz);
+        cut[0] = 0;
+        for (int r = 1; r < P; r++) cut[r] = std::max(cut[r - 1], next_line_start(fd, sz / P * r, sz, false));
+        ::close(fd);
+        for (int r = 0; r < P; r++) if (cut[r + 1] > cut[r]) sh.paf_seg[r].push_back(Segment{paffilenames[k], cut[r], cut[r + 1] - cut[r], false});
+        biggest = std::max(biggest, sz / P + 1);
+    }
+    for (int w = 0; w < 4; w++) {
+        sh.out_fd[w] = ::open((pre + OUT_SUFFIX[w]).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (sh.out_fd[w] < 0) { fprintf(stderr, "raft_b200: cannot open %s%s\n", pre.c_str(), OUT_SUFFIX[w]); destroy_all(); return RAFTGPU_E_IO; }
+    }
+    tm.lap("contexts + input cuts");
+
+    Barrier bar(P);
+    auto    body = [&](int r) {
+        raftgpu_ctx* ctx = sh.ctx[r];
+        int&         rc = sh.status[r];
+        Timer        tr;
+        PinnedPair   pp((size_t)std::max<int64_t>(biggest, 0));
+        rc = pp.ok() ? raftgpu_comm_init(ctx, P, r, sh.comm_id) : RAFTGPU_E_NOMEM;
+        if (bar.wait(rc != 0)) return;
+        // ---- reads
+        if (sh.device_reads) {
+            rc = sh.fasta_seg[r].len > 0 ? ingest_fasta_segments(ctx, pp, {sh.fasta_seg[r]}, (uint64_t)sh.fasta_seg[r].len)
+                                         : raftgpu_ingest_fasta(ctx, nullptr, 0, 1, 0);
+            if (rc == RAFTGPU_OK) rc = raftgpu_reads_info(ctx, &sh.n_local[r], &sh.name_bytes[r], nullptr);
+        }
+        bool bad = sh.device_reads && rc != RAFTGPU_OK && rc != RAFTGPU_E_UNSUPPORTED;
+        if (bar.wait(bad)) return;
+        const bool fallback = bar.wait(sh.device_reads && rc == RAFTGPU_E_UNSUPPORTED) || !sh.device_reads;
+        rc = RAFTGPU_OK;
+        if (!fallback) {
+            if (r == 0) { // global read numbering = file order: prefix sums over the ranks' byte ranges
+                sh.bounds.assign(P + 1, 0); sh.name_base.assign(P + 1, 0);
+                for (int q = 0; q < P; q++) { sh.bounds[q + 1] = sh.bounds[q] + sh.n_local[q]; sh.name_base[q + 1] = sh.name_base[q] + sh.name_bytes[q]; }
+                sh.lengths_all.resize((size_t)sh.bounds[P] + 1); sh.name_off_all.resize((size_t)sh.bounds[P] + 1); sh.names_all.resize((size_t)sh.name_base[P] + 1);
+                sh.hn = sh.bounds[P];
+            }
+            bar.wait();
+            std::vector<int64_t> no((size_t)sh.n_local[r] + 1);
+            rc = raftgpu_reads_copy(ctx, no.data(), sh.names_all.data() + sh.name_base[r], sh.lengths_all.data() + sh.bounds[r]);
+            for (int64_t i = 0; i < sh.n_local[r]; i++) sh.name_off_all[(size_t)(sh.bounds[r] + i)] = sh.name_base[r] + no[(size_t)i];
+            if (r == P - 1) sh.name_off_all[(size_t)sh.bounds[P]] = sh.name_base[P];
+            if (bar.wait(rc != 0)) return;
+            const int64_t* d_seq_off = nullptr;
+            const uint8_t* d_seq = nullptr;
+            rc = raftgpu_reads_device(ctx, &d_seq_off, &d_seq);
+            if (rc == RAFTGPU_OK)
+                rc = raftgpu_set_reads_sharded(ctx, sh.hn, sh.lengths_all.data(), sh.name_off_all.data(), sh.names_all.data(), sh.bounds[r],
+                                               sh.n_local[r], d_seq_off, d_seq);
+        } else {
+            if (r == 0) {
+                rc = raftgpu_load_fasta(readfilename, &sh.hn, &sh.hseq_off, &sh.hseq, &sh.hname_off, &sh.hnames);
+                if (rc == RAFTGPU_OK) {
+                    sh.lengths_all.resize((size_t)sh.hn + 1);
+                    for (int64_t i = 0; i < sh.hn; i++) sh.lengths_all[(size_t)i] = sh.hseq_off[i + 1] - sh.hseq_off[i];
+                    sh.bounds.assign(P + 1, 0);
+                    rc = raftgpu_partition_reads(sh.lengths_all.data(), sh.hn, p->reso, P, sh.bounds.data());
+                }
+            }
+            if (bar.wait(rc != 0)) return;
+            const int64_t b0 = sh.bounds[r], b1 = sh.bounds[r + 1];
+            std::vector<int64_t> own_off((size_t)(b1 - b0) + 1);
+            for (int64_t i = b0; i <= b1; i++) own_off[(size_t)(i - b0)] = sh.hseq_off[i] - sh.hseq_off[b0];
+            rc = raftgpu_set_reads_sharded(ctx, sh.hn, sh.lengths_all.data(), sh.hname_off, sh.hnames, b0, b1 - b0, own_off.data(), sh.hseq + sh.hseq_off[b0]);
+        }
+        if (bar.wait(rc != 0)) return;
+        tr.lap("reads", r);
+        // ---- PAF: the rank's segments stream through the pinned buffers; the first chunk carries the record-0 protocol
+        {
+            ByteSource src(pp, sh.paf_seg[r], true);
+            bool       begun = false, skip = false;
+            for (;;) {
+                const uint8_t* data = nullptr;
+                size_t         fill = 0;
+                bool           last = false;
+                if (!src.next(&data, &fill, &last)) { rc = RAFTGPU_E_IO; break; }
+                if (!begun) { // record 0 of the file is looked for in the first megabytes of the first chunk
+                    const size_t head = std::min<size_t>(fill, 4u << 20);
+                    rc = raftgpu_sharded_begin(ctx, sh.bounds.data(), data, head, last && head == fill ? 1 : 0);
+                    begun = true;
+                    if (rc) { src.release(); break; }
+                }
+                if (!skip) {
+                    const int st2 = raftgpu_ingest_paf(ctx, data, fill, last ? 1 : 0);
+                    if (st2 == RAFTGPU_E_UNKNOWN_NAME || st2 == RAFTGPU_E_RANGE) skip = true; // carried into the finish below: the ranks must still meet
+                    else if (st2) rc = st2;
+                }
+                src.release();
+                if (rc || last) break;
+            }
+        }
+        // a rank that failed outside the data domain cannot take part in the collectives: stop everybody before them
+        if (bar.wait(rc != 0)) return;
+        tr.lap("paf", r);
+        rc = raftgpu_sharded_finish(ctx, &sh.stats[r], &sh.info[r]);
+        if (bar.wait(rc != 0)) return;
+        tr.lap("exchange + run", r);
+        // ---- outputs: this rank's slice of every file, at its file offset
+        std::string err;
+        for (int w = 0; w < 4 && rc == RAFTGPU_OK; w++)
+            if (!write_stream(ctx, w, sh.out_fd[w], sh.info[r].stream_base[w], pp, err)) {
+                std::lock_guard<std::mutex> g(sh.mu);
+                sh.err = err; rc = RAFTGPU_E_IO;
+            }
+        tr.lap("outputs", r);
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < P; r++) th.emplace_back(body, r);
+    for (auto& t : th) t.join();
+    for (int w = 0; w < 4; w++) if (::close(sh.out_fd[w]) != 0 && !sh.status[0]) sh.status[0] = RAFTGPU_E_IO;
+    free(sh.hseq_off); free(sh.hseq); free(sh.hname_off); free(sh.hnames);
+    // the rank with a real error speaks; RAFTGPU_E_PEER only if nobody else does
+    int rc = RAFTGPU_OK, who = -1;
+    for (int r = 0; r < P; r++) if (sh.status[r] && (rc == RAFTGPU_OK || rc == RAFTGPU_E_PEER) ) { rc = sh.status[r]; who = r; }
+    if (rc) {
+        fprintf(stderr, "raft_b200: %s: %s%s\n", raftgpu_strerror(rc), who >= 0 && sh.ctx[who] ? raftgpu_last_error(sh.ctx[who]) : "", sh.err.c_str());
+        destroy_all();
+        return rc;
+    }
+    const raftgpu_shard_info& i0 = sh.info[0];
+    print_run_lines(p, sh.stats[0].real_reads, i0.symmetric, i0.n_records_total, sh.stats[0].high_cov, i0.total_cov, i0.n_bins_total,
+                    i0.total_repeat_len, i0.total_read_len);
+    if (stats_out) {
+        raftgpu_stats s = sh.stats[0];
+        s.n_records = i0.n_records_total; s.symmetric = i0.symmetric; s.total_cov = i0.total_cov; s.total_repeat_len = i0.total_repeat_len;
+        s.total_read_len = i0.total_read_len; s.n_bins = i0.n_bins_total; s.total_windows = (int32_t)(uint32_t)(uint64_t)i0.n_bins_total;
+        s.n_fragments = i0.n_fragments_total; s.n_repeats = 0;
+        for (int r = 0; r < P; r++) s.n_repeats += sh.stats[r].n_repeats;
+        for (int w = 0; w < 4; w++) s.out_bytes[w] = i0.stream_total[w];
+        *stats_out = s;
+    }
+    destroy_all();
+    tm.lap("all ranks");
     return RAFTGPU_OK;
 }

@@ -156,13 +156,7 @@ __device__ __forceinline__ bool parse_record(TextReader& rd, const NameTable& nt
     return true;
 }
 
-__device__ __forceinline__ void report_error(ErrState* err, int code, long long index)
-{
-    // keep the smallest index; the code of that record wins (codes are set once per index race-free enough
-    // for diagnostics: any racing writer carries a real error)
-    long long old = atomicMin(&err->index, index);
-    if (index <= old) err->code = code;
-}
+__device__ __forceinline__ void report_error(ErrState* err, int code, long long index) { err_min(err, code, index); }
 
 // first set bit of mask m at position >= from; the sentinel word makes it return >= K1_STAGE when there is none
 __device__ __forceinline__ int next_bit(const unsigned* m, int from)
@@ -367,9 +361,10 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_paf_tokenize(PafTokArgs a)
     __syncthreads();
 
     // ---- phase B: decode the j-th record of the tile, one per thread
-    int r0[7];
+    int r0[8];
 #pragma unroll
-    for (int k = 0; k < 7; k++) r0[k] = a.rec0[k];
+    for (int k = 0; k < 8; k++) r0[k] = a.rec0[k];
+    const bool first_is_local = a.first_is_local >= 0 ? a.first_is_local != 0 : r0[7] != 0; // sharded runs decide it on the device
     const unsigned* sw = reinterpret_cast<const unsigned*>(s.text);
     const unsigned* tw = reinterpret_cast<const unsigned*>(s.pad_front);
     uint64_t        prefix = 0;
@@ -416,7 +411,7 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_paf_tokenize(PafTokArgs a)
             if (lq >= 0 && lq < a.own_count && !add_interval(a.diff, a.slot_off, lq, pr.qs, pr.qe, a.reso)) err_min(a.err_range, RAFTK_E_RANGE, rec);
         }
         // chop.hpp:171-184: record k >= 1 mirrors record 0
-        if (r0[6] && (rec != 0 || !a.first_is_local) && r0[0] == pr.tid && r0[1] == pr.qid && r0[2] == pr.ts &&
+        if (r0[6] && (rec != 0 || !first_is_local) && r0[0] == pr.tid && r0[1] == pr.qid && r0[2] == pr.ts &&
             r0[3] == pr.te && r0[4] == pr.qs && r0[5] == pr.qe)
             *a.sym_flag = 1;
     }
@@ -424,9 +419,10 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_paf_tokenize(PafTokArgs a)
 }
 
 // First record of the text (single thread; the first line is a record in any sane PAF).
-__global__ void k_paf_peek(const uint8_t* text, int64_t nbytes, NameTable nt, int* rec0, ErrState* err)
+__global__ void k_paf_peek(const uint8_t* text, int64_t nbytes, NameTable nt, int* rec0, ErrState* err, int tail_flag)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    rec0[7] = tail_flag;
     TextReader rd;
     rd.text = text; rd.nbytes = nbytes; rd.stage_lo = 0; rd.stage_len = 0; rd.swords = nullptr; rd.word = 0;
     int64_t ls = 0;
@@ -445,9 +441,9 @@ __global__ void k_paf_peek(const uint8_t* text, int64_t nbytes, NameTable nt, in
     }
 }
 
-void launch_paf_peek(const uint8_t* text, int64_t nbytes, const NameTable& nt, int* rec0, ErrState* err, cudaStream_t st)
+void launch_paf_peek(const uint8_t* text, int64_t nbytes, const NameTable& nt, int* rec0, ErrState* err, cudaStream_t st, int tail_flag)
 {
-    k_paf_peek<<<1, 32, 0, st>>>(text, nbytes, nt, rec0, err);
+    k_paf_peek<<<1, 32, 0, st>>>(text, nbytes, nt, rec0, err, tail_flag);
 }
 
 int paf_tokenize_tiles(int64_t nbytes) { return (int)((nbytes + K1_TILE - 1) / K1_TILE); }

@@ -404,4 +404,46 @@ void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds, 
     k_route_pack<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
 }
 
+__global__ void k_pick_rec0(const int* __restrict__ gathered, int nranks, int rank, int* rec0)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < 8; k++) rec0[k] = 0;
+    for (int r = 0; r < nranks; r++)
+        if (gathered[8 * r + 6]) {
+            for (int k = 0; k < 6; k++) rec0[k] = gathered[8 * r + k];
+            rec0[6] = 1; rec0[7] = r == rank;
+            return;
+        }
+}
+void launch_pick_rec0(const int* gathered, int nranks, int rank, int* rec0, cudaStream_t st) { k_pick_rec0<<<1, 32, 0, st>>>(gathered, nranks, rank, rec0); }
+
+struct Extra4 { long long v[4]; };
+__global__ void k_pack_counts(const unsigned long long* counts, const unsigned long long* list_n, const int* sym_flag, Extra4 ex, int nranks, long long* out)
+{
+    const int k = threadIdx.x;
+    if (k < nranks) out[k] = (long long)counts[k];
+    if (k == 0) { out[nranks] = (long long)*list_n; out[nranks + 1] = *sym_flag; }
+    if (k < 4) out[nranks + 2 + k] = ex.v[k];
+}
+void launch_pack_counts(const unsigned long long* counts, const unsigned long long* list_n, const int* sym_flag, const long long extra[4],
+                        int nranks, long long* out, cudaStream_t st)
+{
+    Extra4 ex{{extra[0], extra[1], extra[2], extra[3]}};
+    k_pack_counts<<<1, 64, 0, st>>>(counts, list_n, sym_flag, ex, nranks, out);
+}
+
+struct ScalarPtrs { const long long* p[8]; };
+__global__ void k_pack_scalars(ScalarPtrs s, int n, const ErrState* err, const ErrState* err_range, long long* out)
+{
+    const int k = threadIdx.x;
+    if (k < n) out[k] = *s.p[k];
+    if (k == 0) { out[n] = (long long)err->packed; out[n + 1] = (long long)err_range->packed; }
+}
+void launch_pack_scalars(const long long* const* src_host, int n, const ErrState* err, const ErrState* err_range, long long* out, cudaStream_t st)
+{
+    ScalarPtrs s{};
+    for (int k = 0; k < n && k < 8; k++) s.p[k] = src_host[k];
+    k_pack_scalars<<<1, 32, 0, st>>>(s, n, err, err_range, out);
+}
+
 } // namespace raftk

@@ -170,8 +170,7 @@ __global__ void __launch_bounds__(256) k_sim_parse(const uint8_t* __restrict__ n
     }
     SimInfo o{};
     if (c1 < 0 || c2 < 0 || eq < 0 || da < 0 || d0 < 0 || c3 < 0) {
-        long long old = atomicMin(&err->index, (long long)gid);
-        if ((long long)gid <= old) err->code = RAFTK_E_SIM_NAME;
+        err_min(err, RAFTK_E_SIM_NAME, (long long)gid);
         out[i] = o;
         return;
     }
@@ -205,8 +204,7 @@ __global__ void __launch_bounds__(256) k_frag_expand(FragExpandArgs a)
         int64_t fa = (j == 0) ? 0 : (int64_t)cuts[j - 1] - a.v;
         int64_t fb = (j == F - 1) ? L : (int64_t)cuts[j];
         if (fa < 0) { // std::string::substr would throw (chop.hpp:318)
-            long long old = atomicMin(&a.err->index, (long long)gid);
-            if ((long long)gid <= old) a.err->code = RAFTK_E_NEG_START;
+            err_min(a.err, RAFTK_E_NEG_START, (long long)gid);
             fa = 0;
         }
         int64_t g = g0 + j;

@@ -11,11 +11,21 @@ namespace raftk {
 // device-side error codes (same numbering as raftgpu_status)
 enum { RAFTK_E_UNKNOWN_NAME = -2, RAFTK_E_DUP_NAME = -3, RAFTK_E_RANGE = -4, RAFTK_E_NEG_START = -5, RAFTK_E_SIM_NAME = -13, RAFTK_E_HASH_COLLISION = -100 };
 
+// First error of a run: (index << 8) | (-code) in ONE word, so that the smallest offending record / read index and
+// its own code are published together by a single atomicMin (ERR_CLEAN when there is none).
 struct ErrState {
-    long long index; // smallest offending record / read index (LLONG_MAX when clean)
-    int       code;
-    int       pad;
+    unsigned long long packed;
+    unsigned long long pad;
 };
+constexpr unsigned long long ERR_CLEAN = ~0ull;
+inline int       err_code(const ErrState& e) { return -(int)(e.packed & 0xffull); }
+inline long long err_index(const ErrState& e) { return (long long)(e.packed >> 8); }
+#ifdef __CUDACC__
+__device__ __forceinline__ void err_min(ErrState* err, int code, long long index)
+{
+    atomicMin(&err->packed, ((unsigned long long)index << 8) | (unsigned long long)(unsigned)(-code));
+}
+#endif
 
 // ---------------------------------------------------------------- name table (nametable.cu)
 cudaError_t launch_name_build(NameTable* out_table_desc_host, void* slots, unsigned long long capacity, unsigned long long seed,
@@ -60,8 +70,8 @@ struct PafTokArgs {
     int64_t        rec_base, rec_cap;
     int32_t *      qid, *tid, *qs, *qe, *ts, *te;
     uint8_t*       strand;
-    const int*     rec0;          // device int[7]: qid,tid,qs,qe,ts,te,present
-    int            first_is_local; // record index 0 of this context is the file's record 0
+    const int*     rec0;          // device int[8]: qid,tid,qs,qe,ts,te,present,first_is_local
+    int            first_is_local; // record index 0 of this context is the file's record 0 (1 / 0); -1: read rec0[7] on the device
     int            n_tiles;
     uint64_t*      status;        // n_tiles words, zeroed
     int*           ticket;        // zeroed
@@ -79,7 +89,8 @@ struct PafTokArgs {
 
 int         paf_tokenize_tiles(int64_t nbytes);
 cudaError_t launch_paf_tokenize(const PafTokArgs& a, cudaStream_t st);
-void        launch_paf_peek(const uint8_t* text, int64_t nbytes, const NameTable& nt, int* rec0, ErrState* err, cudaStream_t st);
+// first record of the text into rec0[0..6] (rec0[6] = found); rec0[7] = tail_flag (the caller's "this was my whole text")
+void        launch_paf_peek(const uint8_t* text, int64_t nbytes, const NameTable& nt, int* rec0, ErrState* err, cudaStream_t st, int tail_flag = 0);
 
 // ---------------------------------------------------------------- layout + K2 (k2_coverage.cu)
 // per owned read: slots = nb+1, repeat capacity, cut capacity  (int32 each)
@@ -126,6 +137,14 @@ void launch_route_collect(const ScatterArgs& a, int nranks, const int64_t* bound
 void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cursors_dev, int32_t* sendbuf, cudaStream_t st);
 void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds_dev, unsigned long long* cursors_dev, int32_t* sendbuf,
                        cudaStream_t st);
+// sharded runs inside the library (NCCL): tiny glue kernels around the collectives, so that no host round trip sits between them
+// gathered = nranks x 8 ints (qid,tid,qs,qe,ts,te,found,whole_text_peeked): rec0 <- the first rank that found a record, rec0[7] = it is `rank`
+void launch_pick_rec0(const int* gathered, int nranks, int rank, int* rec0, cudaStream_t st);
+// out[0..nranks) = counts, out[nranks] = list_n, out[nranks+1] = *sym_flag, out[nranks+2..nranks+6) = extra (host scalars)
+void launch_pack_counts(const unsigned long long* counts, const unsigned long long* list_n, const int* sym_flag, const long long extra[4],
+                        int nranks, long long* out, cudaStream_t st);
+// out[0..n) = *src[k] (scalars scattered over device memory), then the two error words
+void launch_pack_scalars(const long long* const* src_host, int n, const ErrState* err, const ErrState* err_range, long long* out, cudaStream_t st);
 
 // ---------------------------------------------------------------- K3 (k3_repeat_cut.cu)
 struct RepeatCutArgs {

@@ -33,8 +33,7 @@ __global__ void k_name_verify(NameTable t, const uint8_t* names, const int64_t* 
         for (int64_t k = 0; same && k < la; k++) same = names[a + k] == names[b + k];
     }
     int       code = same ? RAFTK_E_DUP_NAME : RAFTK_E_HASH_COLLISION;
-    long long old = atomicMin(&err->index, (long long)i);
-    if ((long long)i <= old) err->code = code;
+    err_min(err, code, (long long)i);
 }
 
 __global__ void k_name_clear(NameSlot* slots, unsigned long long cap)

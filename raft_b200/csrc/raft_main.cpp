@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "../../include/raft_b200.h"
 
@@ -66,10 +67,26 @@ int main(int argc, char* argv[])
     std::cout.flush();
 
     const char* dev_env = getenv("RAFT_B200_DEVICE");
-    // extension over main.cpp:75 (whose third positional argument is unused): any further positional arguments are
-    // more PAF files, ingested back to back as `cat` would join them (README.md:35-36 merges hifiasm's two files)
-    int         st = raftgpu_break_long_reads_multi(argv[optind], argc - optind - 1, argv + optind + 1, &p, prefix.c_str(),
-                                                    dev_env ? atoi(dev_env) : 0, nullptr);
+    // RAFT_B200_DEVICES=0,1,...,7: the run is sharded over these GPUs (reads by id range, PAF by byte range, NCCL exchange)
+    std::vector<int> devs;
+    if (const char* e = getenv("RAFT_B200_DEVICES")) {
+        for (const char* q = e; *q;) {
+            char* end = nullptr;
+            long  v = strtol(q, &end, 10);
+            if (end == q) break;
+            devs.push_back((int)v);
+            q = *end == ',' ? end + 1 : end;
+        }
+    }
+    // main.cpp:75 passes argv[optind+2] on and break_long_reads ignores it (chop.hpp:331): so do we.  Opt-in extension:
+    // with RAFT_B200_MULTI_PAF=1 every further positional argument is one more PAF file, ingested back to back as `cat`
+    // would join them (README.md:35-36 merges hifiasm's two *.ovlp.paf files before calling raft).
+    const char* multi = getenv("RAFT_B200_MULTI_PAF");
+    const int   n_paf = (multi && atoi(multi) != 0) ? argc - optind - 1 : 1;
+    int         st = devs.size() > 1 ? raftgpu_break_long_reads_mgpu(argv[optind], n_paf, argv + optind + 1, &p, prefix.c_str(), (int)devs.size(),
+                                                                     devs.data(), nullptr)
+                                     : raftgpu_break_long_reads_multi(argv[optind], n_paf, argv + optind + 1, &p, prefix.c_str(),
+                                                                      devs.size() == 1 ? devs[0] : (dev_env ? atoi(dev_env) : 0), nullptr);
     fflush(stdout);
     if (st == RAFTGPU_E_IO) return 1; // chop.hpp:339-348 exit(1)
     if (st != RAFTGPU_OK) return 2;   // inputs on which the reference crashes (segfault / SIGFPE / throw) or CUDA failure

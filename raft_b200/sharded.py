@@ -154,49 +154,56 @@ def run_rank(engine, comm, bounds, text, nbytes):
 
 # ------------------------------------------------------------------------------------------- bench (N > 1)
 def bench(a, rank, world, local, log):
-    """Strong-scaling bench (BASELINE.json configs[2]): the SAME human-scale reads + PAF as the 1-GPU run, reads sharded by
-    id range and the PAF split by byte range over `world` GPUs."""
+    """Strong-scaling bench (BASELINE.json configs[2]): the SAME inputs as the 1-GPU run, reads sharded by id range and the
+    PAF split by line range over `world` GPUs.  The sharded path runs inside the library (raftgpu_run_sharded: NCCL
+    collectives + ncclSend/ncclRecv on the library stream); torch.distributed only carries the communicator id, the
+    barriers around the timed region and the reduction of the reported numbers."""
     import json
     import os
     import torch
     import torch.distributed as dist
     from . import api, synth_gpu
+    import bench as B
 
     dev = torch.device("cuda", local)
     comm = TorchComm(dist, dev)
     WINDOW = 1 << 30
-    ds = synth_gpu.make_dataset_gpu(a.config, a.scale, device=f"cuda:{local}", with_seq=False, line_slice=(rank, world))
+    sym = not a.asymmetric
+    ds = synth_gpu.make_dataset_gpu(a.config, a.scale, symmetric=sym, device=f"cuda:{local}", with_seq=False, line_slice=(rank, world))
     p = api.AlgoParams.from_args(ds.args)
     lengths = ds.lengths.cpu().numpy()
-    bounds = partition_reads(lengths, p.reso, world)
+    bounds = api.partition_reads(lengths, p.reso, world)
     b0, b1 = int(bounds[rank]), int(bounds[rank + 1])
     own_seq = synth_gpu.gen_seq(ds, b0, b1)
     own_off = (ds.seq_off[b0:b1 + 1] - ds.seq_off[b0]).contiguous()
     torch.cuda.synchronize()
     log(f"[bench r{rank}] reads {b0}..{b1} of {ds.n}, {own_seq.numel()} bases, local PAF {ds.paf.numel()} bytes / {ds.n_overlaps} lines")
     ctx = api.Context(p, local)
+    ids = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(world, rank, ids[0])
     win = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
     win2 = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
+    OUTS = (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA)
 
     def step(host=None):
         if host is None:
             ctx.set_reads_sharded(ds.n, ds.lengths, ds.name_off, ds.names, b0, b1 - b0, own_off, own_seq)
-            st, info = run_rank(ctx, comm, bounds, ds.paf, ds.paf.numel())
-            dst = win
+            st, info = ctx.run_sharded(bounds, ds.paf, ds.paf.numel())
         else:
             ctx.set_reads_sharded(ds.n, host["lengths"], host["name_off"], host["names"], b0, b1 - b0, host["own_off"], host["own_seq"])
-            st, info = run_rank(ctx, comm, bounds, host["paf"], ds.paf.numel())
-            dst = host["out"].data_ptr()
+            st, info = ctx.run_sharded(bounds, host["paf"], ds.paf.numel())
         nout = 0
         if host is None:  # device windows: text streams and the gather overlap on the library's two emit streams
-            for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+            for which in OUTS:
                 n = ctx.output_size(which)
                 for off in range(0, n, WINDOW):
                     ctx.fetch_async(which, off, win2 if which != api.OUT_READS_FASTA else win, min(WINDOW, n - off))
                 nout += n
             ctx.sync()
         else:
-            for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA):
+            dst = host["out"].data_ptr()
+            for which in OUTS:
                 n = ctx.output_size(which)
                 for off in range(0, n, WINDOW):
                     ctx.fetch_into(which, off, dst, min(WINDOW, n - off))
@@ -217,10 +224,16 @@ def bench(a, rank, world, local, log):
         dist.barrier()
         return float(t), st, info, nout
 
+    def all_digests(info):
+        """file digests = sum over ranks of the slice digests taken at their file offsets (mod 2^64); sizes = the gathered totals"""
+        mine = [ctx.digest(w, int(info.stream_base[w])) for w in OUTS]
+        allv = comm.all_gather_i64([v - (1 << 64) if v >= (1 << 63) else v for v in mine])
+        tot = [int(sum(int(x) for x in allv[:, k])) % (1 << 64) for k in range(3)]
+        return {name: [int(info.stream_total[w]), tot[k]] for k, (w, name) in enumerate(zip(OUTS, B.STREAMS))}
+
     for _ in range(a.warmup):
         step()
-    from bench import ClockSampler
-    clocks = ClockSampler(local)
+    clocks = B.ClockSampler(local)
     if rank == 0:
         clocks.start()
     ms, st, info, nout = timed(a.steps)
@@ -228,11 +241,20 @@ def bench(a, rank, world, local, log):
     s2 = ctx.stats()
     frag = ctx.table(api.TAB_FRAG).reshape(-1, 3)
     fasta_alg = int((frag[:, 2].astype(np.int64) - frag[:, 1]).sum()) + ctx.output_size(api.OUT_READS_FASTA)  # bases gathered + bytes written
+    del frag
     launches = s2.kernel_launches * a.steps
     fasta_ms = s2.ms_emit[3]
-    stage = {"set_reads": s2.ms_set_reads, "tokenize": s2.ms_tokenize, "scatter": s2.ms_scatter, "scan": s2.ms_scan, "repeat_cut": s2.ms_repeat_cut,
+    stage = {"set_reads": s2.ms_set_reads, "tokenize": s2.ms_tokenize, "exchange": info.ms_exchange, "scan": s2.ms_scan, "repeat_cut": s2.ms_repeat_cut,
              "layout": s2.ms_layout, "emit_cov": s2.ms_emit[0], "emit_rep": s2.ms_emit[1], "emit_fasta": s2.ms_emit[3]}
-    tot = comm.all_gather_i64([info["sent_remote"], nout, int(own_seq.numel()), int(ds.paf.numel()), launches])
+    tot = comm.all_gather_i64([int(info.endpoints_sent), nout, int(own_seq.numel()), int(ds.paf.numel()), launches])
+    # ---- parity (not timed): the files the ranks' slices add up to, against the oracle-verified digests of the 1-GPU run
+    checks = []
+    dig = all_digests(info)
+    key = B.digest_key(a)
+    exp, exp_src = B.load_expected(key)
+    if exp is not None:
+        checks.append({"what": f"{world}-GPU run (NCCL inside the library) vs the recorded digests of the oracle-verified 1-GPU run of the same inputs",
+                       "vs": "n1", "source": exp_src, "scale": a.scale, "identical": exp == dig})
     e2e = None
     if not a.no_e2e:
         def pinned(t):
@@ -245,11 +267,14 @@ def bench(a, rank, world, local, log):
         ctx.set_option(api.OPT_DEFER_SEQ_UPLOAD, 1)
         step(host)
         k = max(1, min(a.steps, 3))
-        ms_e, _, _, nout_e = timed(k, host)
+        ms_e, _, info_e, nout_e = timed(k, host)
         h2d = sum(int(v.nbytes) for kk, v in host.items() if kk != "out")
         io = comm.all_gather_i64([h2d, nout_e])
-        e2e = {"value": info["n_records_total"] / (ms_e / 1e3), "unit": "overlaps/s", "h2d_bytes_per_step": int(io[:, 0].sum()),
+        e2e = {"value": info.n_records_total / (ms_e / 1e3), "unit": "overlaps/s", "h2d_bytes_per_step": int(io[:, 0].sum()),
                "d2h_bytes_per_step": int(io[:, 1].sum()), "ms_per_step": ms_e, "steps": k}
+        dig_e = all_digests(info_e)
+        checks.append({"what": "e2e run (pinned host inputs through the C ABI on every rank) vs the device-resident run", "vs": "n-gpu device-resident",
+                       "scale": a.scale, "identical": dig_e == dig})
     if rank == 0:
         peaks = {}
         try:
@@ -258,19 +283,21 @@ def bench(a, rank, world, local, log):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         bytes_alg = int(tot[:, 1].sum() + tot[:, 2].sum() + tot[:, 3].sum()) + world * int(ds.names.numel())
-        out = {"metric": "PAF overlaps/sec end-to-end fragmentation", "value": info["n_records_total"] / (ms / 1e3), "unit": "overlaps/s",
+        best = checks[0] if checks else None
+        parity = {"identical": all(c["identical"] for c in checks) if checks else None, "scale": best["scale"] if best else None,
+                  "vs": best["vs"] if best else None, "digests": dig, "checks": checks}
+        out = {"metric": "PAF overlaps/sec end-to-end fragmentation", "value": info.n_records_total / (ms / 1e3), "unit": "overlaps/s",
                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
-               "config": {"workload": f"{a.config} synthetic human 32x ONT-Duplex-shaped reads + symmetric all-vs-all PAF, genome scale {a.scale:g} "
-                                      f"(the same inputs as the 1-GPU run), reads sharded by id range over {world} B200, PAF split by byte range, "
-                                      f"NCCL all-to-all routing",
-                          "n_overlaps": info["n_records_total"], "n_reads": ds.n, "bases": int(tot[:, 2].sum()),
-                          "paf_bytes": int(tot[:, 3].sum()), "out_bytes_total": int(tot[:, 1].sum()),
-                          "exchange": {"endpoints_sent_to_other_ranks": int(tot[:, 0].sum()), "bytes": 12 * int(tot[:, 0].sum()),
-                                       "collective": "all_to_all_single (NCCL) of 12-byte endpoints + counts"},
-                          "l2": "inputs and outputs are GBs per rank (>> 126 MB L2); no explicit flush"},
+               "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic", "config": B.config_block(a, ds.args),
+               "workload_sizes": {"n_overlaps": int(info.n_records_total), "n_reads": ds.n, "bases": int(tot[:, 2].sum()), "paf_bytes": int(tot[:, 3].sum()),
+                                  "out_bytes": {name: v[0] for name, v in dig.items()}, "symmetric": int(info.symmetric),
+                                  "n_fragments": int(info.n_fragments_total)},
+               "sharding": {"how": f"the same inputs as the 1-GPU run: reads sharded by id range (balanced by coverage slots) over {world} B200, PAF split by "
+                                   f"line range, exchange inside the library (raftgpu_run_sharded)",
+                            "collectives": "ncclAllGather(record 0), ncclAllReduce(symmetric), ncclAllGather(counts), grouped ncclSend/ncclRecv(12-byte endpoints), "
+                                           "ncclAllGather(fragment counts), ncclAllGather(output sizes)",
+                            "endpoints_sent_to_other_ranks": int(tot[:, 0].sum()), "exchange_bytes": 12 * int(tot[:, 0].sum())},
                "gbp_per_s": int(tot[:, 2].sum()) / (ms / 1e3) / 1e9, "stage_ms_rank0": stage,
-               "protocol_ms_rank0": {k: round(v, 3) for k, v in info["phase_ms"].items()},
                "roofline": {"kernel": "k_fasta_emit", "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
                             "achieved": None if not fasta_ms else fasta_alg / (fasta_ms / 1e3) / 1e9,
                             "frac": None if not fasta_ms else fasta_alg / (fasta_ms / 1e3) / 1e9 / peak,
@@ -278,8 +305,10 @@ def bench(a, rank, world, local, log):
                             "note": "rank 0's gather kernel over its own slice: bases gathered + reads.fasta bytes written, CUDA events on the library stream"},
                "path_roofline": {"bytes_alg": bytes_alg, "achieved_gbs_per_gpu": bytes_alg / world / (ms / 1e3) / 1e9,
                                  "frac": bytes_alg / world / (ms / 1e3) / 1e9 / peak},
-               "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(tot[:, 4].sum()), "clocks": clk}
+               "parity": parity, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(tot[:, 4].sum()), "clocks": clk}
         print(json.dumps(out), flush=True)
+        if parity["identical"] is False:
+            log("[bench] PARITY CHECK FAILED: " + json.dumps(checks))
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

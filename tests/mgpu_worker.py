@@ -20,7 +20,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0")) % ngpu
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if backend == "nccl":
+    if backend == "lib":      # the library's own NCCL communicator; torch.distributed only hands the id around
+        dist.init_process_group("gloo")
+        comm = None
+    elif backend == "nccl":
         dist.init_process_group("nccl", device_id=dev)
         comm = sharded.TorchComm(dist, dev)
     else:
@@ -39,7 +42,19 @@ def main():
     ctx.set_reads_sharded(ds.reads.n, lens, np.ascontiguousarray(ds.reads.name_off, np.int64), np.ascontiguousarray(ds.reads.names, np.uint8),
                           b0, b1 - b0, own_off, own_seq)
     text = np.frombuffer(paf[lo:hi], np.uint8)
-    st, info = sharded.run_rank(ctx, comm, bounds, text, hi - lo)
+    if backend == "lib":
+        ids = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+        assert np.array_equal(bounds, api.partition_reads(lens, p.reso, world))  # the C and the Python partition agree
+        st, sh = ctx.run_sharded(bounds, text, hi - lo)
+        info = dict(symmetric=sh.symmetric, n_records_total=sh.n_records_total, sent_remote=sh.endpoints_sent, received=sh.endpoints_received,
+                    first_read_num=sh.first_read_num, n_fragments_total=sh.n_fragments_total, stream_base=list(sh.stream_base),
+                    stream_total=list(sh.stream_total), backend="nccl-lib", peek_retries=sh.peek_retries,
+                    digest=[ctx.digest(w, sh.stream_base[w]) for w in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA)])
+    else:
+        st, info = sharded.run_rank(ctx, comm, bounds, text, hi - lo)
+        info["backend"] = backend
     out = dict(info=info, cov=ctx.fetch(api.OUT_COVERAGE), rep=ctx.fetch(api.OUT_LONG_REPEATS), fasta=ctx.fetch(api.OUT_READS_FASTA),
                frag=ctx.table(api.TAB_FRAG).reshape(-1, 3), bin_cov=ctx.table(api.TAB_COV))
     torch.save(out, os.path.join(outdir, f"r{rank}.pt"))

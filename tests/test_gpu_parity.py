@@ -199,8 +199,9 @@ def test_cli_two_paf_files_equal_cat():
         open(os.path.join(d, "a.paf"), "wb").write(paf[:cut])
         with gzip.open(os.path.join(d, "b.paf.gz"), "wb") as f:
             f.write(paf[cut:])
+        multi = dict(os.environ, RAFT_B200_MULTI_PAF="1")   # the extension is opt-in: the reference ignores a third positional argument
         r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "out"), os.path.join(d, "r.fa"), os.path.join(d, "a.paf"),
-                                                    os.path.join(d, "b.paf.gz")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+                                                    os.path.join(d, "b.paf.gz")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, env=multi)
         assert r.returncode == 0, r.stdout.decode()
         for suf in SUFS:
             check_output(entry, suf, open(os.path.join(d, "out." + suf), "rb").read())
@@ -213,8 +214,24 @@ def test_cli_two_paf_files_equal_cat():
             check_output(entry, suf, open(os.path.join(d, "py." + suf), "rb").read())
         # a missing second file is reported like a missing first one (chop.hpp:344-348)
         r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "o2"), os.path.join(d, "r.fa"), os.path.join(d, "a.paf"),
-                                                    os.path.join(d, "nope.paf")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+                                                    os.path.join(d, "nope.paf")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, env=multi)
         assert r.returncode == 1 and b"nope.paf input file either does not exist or is empty" in r.stdout
+        # without the opt-in a third positional argument is ignored, as in the reference (main.cpp:75, chop.hpp:331)
+        open(os.path.join(d, "whole.paf"), "wb").write(paf)
+        r = subprocess.run([exe] + entry["args"] + ["-o", os.path.join(d, "o3"), os.path.join(d, "r.fa"), os.path.join(d, "whole.paf"),
+                                                    os.path.join(d, "nope.paf")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+        assert r.returncode == 0, r.stdout.decode()
+        for suf in SUFS:
+            check_output(entry, suf, open(os.path.join(d, "o3." + suf), "rb").read())
+        # a file without a final newline does not glue its last record to the first line of the next file
+        lines = paf.split(b"\n")
+        half = len(lines) // 2
+        open(os.path.join(d, "c.paf"), "wb").write(b"\n".join(lines[:half]))          # no trailing newline
+        open(os.path.join(d, "e.paf"), "wb").write(b"\n".join(lines[half:]))
+        p2 = api.AlgoParams.from_args(entry["args"] + ["-o", os.path.join(d, "py2")])
+        api.break_long_reads(os.path.join(d, "r.fa"), [os.path.join(d, "c.paf"), os.path.join(d, "e.paf")], p2)
+        for suf in SUFS:
+            check_output(entry, suf, open(os.path.join(d, "py2." + suf), "rb").read())
 
 
 def test_async_fetch_lanes():
