@@ -237,12 +237,21 @@ def emit_all_device(ctx, api, win, win2):
     """materialise every output stream into device window buffers, window by window.  The text streams go to `win2`
     and the sequence stream to `win` through the asynchronous API: they run on two CUDA streams of the library."""
     sizes = {w: ctx.output_size(w) for w in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA)}
-    for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS):
-        for off in range(0, sizes[which], WINDOW):
-            ctx.fetch_async(which, off, win2, min(WINDOW, sizes[which] - off))
     n = sizes[api.OUT_READS_FASTA]
-    for off in range(0, n, WINDOW):
-        ctx.fetch_async(api.OUT_READS_FASTA, off, win, min(WINDOW, n - off))
+
+    def text():
+        for which in (api.OUT_COVERAGE, api.OUT_LONG_REPEATS):
+            for off in range(0, sizes[which], WINDOW):
+                ctx.fetch_async(which, off, win2, min(WINDOW, sizes[which] - off))
+
+    def fasta():
+        for off in range(0, n, WINDOW):
+            ctx.fetch_async(api.OUT_READS_FASTA, off, win, min(WINDOW, n - off))
+
+    if os.environ.get("RAFT_B200_EMIT_ORDER") == "fasta_first":
+        fasta(); text()
+    else:
+        text(); fasta()
     ctx.sync()
     return sum(sizes.values())
 

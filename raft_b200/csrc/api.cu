@@ -115,6 +115,7 @@ struct raftgpu_ctx {
     DevBuf  b_rep_off, b_rep_line_size, b_rep_line_off, b_cov_tile_bytes, b_cov_tile_static, b_cov_tile_off, b_cov_tile_read, b_fasta_tile_frag, b_frag_desc;
     std::vector<int64_t> h_cov_tile_off, h_rep_line_off; // every OFF_SAMPLE-th entry of the device tables (+ the last)
     DevBuf  b_off_sample, b_sim, b_bed_line_size, b_bed_line_off;
+    DevBuf  b_cov_tabs; bool cov_tabs_built = false; // text tables of the coverage.txt emitter (depend on -r only)
     std::vector<int64_t> h_bed_line_off;
     int64_t G = 0, n_repeats = 0, read_num_base = 0;
     raftgpu_stats stats{};
@@ -1570,6 +1571,15 @@ static int emit_window_impl(raftgpu_ctx* ctx, int which, int64_t w0, int64_t w1,
         ca.cov = ctx->b_cov.as<int32_t>(); ca.slot_off = ctx->b_slot_off.as<int64_t>(); ca.m = m; ca.n_slots = ctx->n_slots;
         ca.own_first = ctx->own_first; ca.reso = ctx->prm.reso; ca.tile_off = ctx->b_cov_tile_off.as<int64_t>();
         ca.dst = d; ca.w0 = w0; ca.w1 = w1; ca.tile_first = t0; ca.tile_read = ctx->b_cov_tile_read.as<int32_t>();
+        if (!ctx->cov_tabs_built) {
+            CK(ctx->b_cov_tabs.ensure(sizeof(unsigned long long) * COV_POS_TAB_ENTRIES + sizeof(unsigned) * COV_TAB_ENTRIES));
+            launch_cov_tables(ctx->b_cov_tabs.as<unsigned long long>(), COV_POS_TAB_ENTRIES, ctx->prm.reso,
+                              reinterpret_cast<unsigned*>(ctx->b_cov_tabs.as<unsigned long long>() + COV_POS_TAB_ENTRIES), st);
+            CKL();
+            ctx->cov_tabs_built = true;
+        }
+        ca.pos_tab = ctx->b_cov_tabs.as<unsigned long long>(); ca.tab_n = COV_POS_TAB_ENTRIES;
+        ca.cov_tab = reinterpret_cast<const unsigned*>(ctx->b_cov_tabs.as<unsigned long long>() + COV_POS_TAB_ENTRIES);
         launch_cov_emit(ca, t1 - t0, st);
         CKL();
     } else if (which == RAFTGPU_OUT_LONG_REPEATS) {

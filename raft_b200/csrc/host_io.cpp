@@ -154,7 +154,7 @@ struct PinnedPair {
     size_t   cap = 0;
     explicit PinnedPair(size_t want)
     {
-        cap = std::min<size_t>(256u << 20, std::max<size_t>(want, 1u << 20));
+        cap = std::min<size_t>(64u << 20, std::max<size_t>(want, 1u << 20)); // 64 MiB chunks keep every pipe busy; pinning costs ~0.4 ms per MiB
         cap = (cap + 4095) & ~(size_t)4095;
         for (int k = 0; k < 2; k++) {
             void* p = nullptr;
@@ -169,6 +169,68 @@ struct PinnedPair {
     }
     bool ok() const { return buf[0] && buf[1]; }
 };
+
+// Page-cache / tmpfs copies run at a few GB/s per thread: large transfers are cut into slices moved by a few threads.
+constexpr size_t IO_SLICE = 16u << 20;
+constexpr int    IO_THREADS = 4;
+// pread of [pos, pos+want) into dst; returns the bytes read (short only at the end of the file), -1 on error
+long parallel_pread(int fd, uint8_t* dst, size_t want, int64_t pos)
+{
+    if (want < 2 * IO_SLICE) {
+        size_t got = 0;
+        while (got < want) {
+            ssize_t r = pread(fd, dst + got, want - got, (off_t)(pos + (int64_t)got));
+            if (r < 0) return -1;
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        return (long)got;
+    }
+    const int    T = (int)std::min<size_t>(IO_THREADS, want / IO_SLICE);
+    const size_t per = ((want + T - 1) / T + 4095) & ~(size_t)4095;
+    std::vector<long>        res(T, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([&, t] {
+            const size_t lo = std::min(want, per * t), hi = std::min(want, per * (t + 1));
+            size_t       got = 0;
+            while (lo + got < hi) {
+                ssize_t r = pread(fd, dst + lo + got, hi - lo - got, (off_t)(pos + (int64_t)(lo + got)));
+                if (r < 0) { res[t] = -1; return; }
+                if (r == 0) break;
+                got += (size_t)r;
+            }
+            res[t] = (long)got;
+        });
+    for (auto& x : th) x.join();
+    long total = 0;
+    for (int t = 0; t < T; t++) {
+        if (res[t] < 0) return -1;
+        total += res[t];
+        if ((size_t)res[t] < std::min(want, per * (t + 1)) - std::min(want, per * t)) break; // end of file inside this slice
+    }
+    return total;
+}
+bool parallel_pwrite(int fd, const uint8_t* src, size_t n, uint64_t at)
+{
+    auto put = [&](size_t lo, size_t hi) {
+        while (lo < hi) {
+            ssize_t w = pwrite(fd, src + lo, hi - lo, (off_t)(at + lo));
+            if (w <= 0) return false;
+            lo += (size_t)w;
+        }
+        return true;
+    };
+    if (n < 2 * IO_SLICE) return put(0, n);
+    const int    T = (int)std::min<size_t>(IO_THREADS, n / IO_SLICE);
+    const size_t per = ((n + T - 1) / T + 4095) & ~(size_t)4095;
+    std::vector<char>        ok(T, 1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&, t] { ok[t] = put(std::min(n, per * t), std::min(n, per * (t + 1))) ? 1 : 0; });
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; t++) if (!ok[t]) return false;
+    return true;
+}
 
 // One piece of input: bytes [off, off+len) of a plain file (len < 0: to the end), or a whole gzip file.
 struct Segment { std::string path; int64_t off = 0, len = -1; bool gz = false; };
@@ -261,7 +323,7 @@ private:
                     got = gzread(gz, pp_.buf[k] + fill, (unsigned)std::min<size_t>(CAP - fill, 1u << 30));
                 } else {
                     const size_t want = (size_t)std::min<int64_t>((int64_t)(CAP - fill), end - pos);
-                    got = want ? (long)pread(fd, pp_.buf[k] + fill, want, (off_t)pos) : 0;
+                    got = want ? parallel_pread(fd, pp_.buf[k] + fill, want, pos) : 0;
                     if (got > 0) pos += got;
                 }
                 if (got < 0) { close_cur(gz, fd); fail(); return; }
@@ -352,11 +414,7 @@ static bool write_stream(raftgpu_ctx* ctx, int which, int fd, uint64_t file_base
             cv.wait(g, [&] { return full[k] || done; });
             if (!full[k]) return;
             g.unlock();
-            size_t put = 0;
-            while (!werr && put < len[k]) {
-                ssize_t w = pwrite(fd, pp.buf[k] + put, len[k] - put, (off_t)(at[k] + put));
-                if (w <= 0) werr = true; else put += (size_t)w;
-            }
+            if (!werr && !parallel_pwrite(fd, pp.buf[k], len[k], at[k])) werr = true;
             g.lock();
             full[k] = false;
             cv.notify_all();
@@ -532,7 +590,9 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
         tm.lap(OUT_SUFFIX[w]);
     }
     if (stats_out) *stats_out = s;
-    raftgpu_destroy(ctx);
+    // A process that exits right after the call (the `raft` CLI) can leave the teardown of tens of GB of device buffers
+    // to the driver's process cleanup instead of paying for it buffer by buffer (the reference frees nothing either).
+    if (!getenv("RAFT_B200_NO_TEARDOWN")) raftgpu_destroy(ctx);
     tm.lap("destroy");
     return RAFTGPU_OK;
 }
@@ -660,13 +720,36 @@ extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf
     }
     tm.lap("contexts + input cuts");
 
+    // The communicator is built first, by one short-lived thread per rank, with stdout pointed at stderr meanwhile: NCCL
+    // prints its version banner on stdout at the first initialisation (NCCL_DEBUG=VERSION), and the reference's stdout
+    // lines are part of the drop-in contract.
+    {
+        fflush(stdout);
+        const int saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+        std::vector<std::thread> ci;
+        for (int r = 0; r < P; r++) ci.emplace_back([&, r] { sh.status[r] = raftgpu_comm_init(sh.ctx[r], P, r, sh.comm_id); });
+        for (auto& t : ci) t.join();
+        fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        for (int r = 0; r < P; r++)
+            if (sh.status[r]) {
+                fprintf(stderr, "raft_b200: device %d: %s: %s\n", devices[r], raftgpu_strerror(sh.status[r]), raftgpu_last_error(sh.ctx[r]));
+                st = sh.status[r];
+                for (int w = 0; w < 4; w++) ::close(sh.out_fd[w]);
+                destroy_all();
+                return st;
+            }
+    }
+    tm.lap("communicator");
+
     Barrier bar(P);
     auto    body = [&](int r) {
         raftgpu_ctx* ctx = sh.ctx[r];
         int&         rc = sh.status[r];
         Timer        tr;
         PinnedPair   pp((size_t)std::max<int64_t>(biggest, 0));
-        rc = pp.ok() ? raftgpu_comm_init(ctx, P, r, sh.comm_id) : RAFTGPU_E_NOMEM;
+        rc = pp.ok() ? RAFTGPU_OK : RAFTGPU_E_NOMEM;
         if (bar.wait(rc != 0)) return;
         // ---- reads
         if (sh.device_reads) {
@@ -779,7 +862,7 @@ extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf
         for (int w = 0; w < 4; w++) s.out_bytes[w] = i0.stream_total[w];
         *stats_out = s;
     }
-    destroy_all();
+    if (!getenv("RAFT_B200_NO_TEARDOWN")) destroy_all();
     tm.lap("all ranks");
     return RAFTGPU_OK;
 }

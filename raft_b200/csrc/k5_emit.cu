@@ -34,6 +34,14 @@ constexpr int CW_CHUNK = 32 * CW_PER;
 constexpr int CW_BUF = 2048;          // per-warp text buffer
 constexpr int CW_CAP = CW_BUF - 16;   // chunks with more text (tiny reads: many "read i " prefixes) take the direct path
 constexpr int CW_MAX_SLOT_BYTES = 40; // "read 2147483647 " (16) + "2147483647,-2147483648 " (23)
+// Fast lanes (all four slots are ordinary bins of one read): the text of a bin is   <k*reso> ',' <cov> ' '   and both halves
+// come from tables -- the position text of bin k does not depend on the data (one 8-byte entry per k: the digits and the
+// comma in the low bytes, their count in the top byte; built once per context), the coverage text of values below 1000
+// sits in shared memory.  A slot's <= 11 bytes are composed in three registers, shifted to the lane's running byte phase
+// and stored as whole 32-bit words; only the lane's first and last partial word go out byte by byte.  Lanes that hold a
+// read boundary (a sentinel, a "read i " prefix), a coverage outside [0, 1000) or a bin beyond the table take the generic
+// digit-by-digit path below.
+constexpr int CT_COV = 1024;          // coverage-text table entries (values 0..999 are used)
 
 // ASCII of the four decimal digits of n < 10000, most significant digit in the low byte
 __device__ __forceinline__ unsigned ascii4(unsigned n)
@@ -84,11 +92,11 @@ __device__ __forceinline__ uint8_t* cov_slot_format(uint8_t* p, bool first, bool
     return p + dcov + 1;
 }
 // rare (dozens of tiny reads in one chunk): format privately, store byte-wise with clipping
-__device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int whi, bool first, bool sentinel, bool neg, unsigned pos, int dpos,
-                                            unsigned ucov, int dcov, unsigned read_id)
+__device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int whi, bool first, bool sentinel, bool neg, unsigned pos, unsigned ucov,
+                                            unsigned read_id)
 {
     uint8_t  loc[CW_MAX_SLOT_BYTES];
-    uint8_t* e = cov_slot_format(loc, first, sentinel, neg, pos, dpos, ucov, dcov, read_id);
+    uint8_t* e = cov_slot_format(loc, first, sentinel, neg, pos, dec_digits(pos), ucov, dec_digits(ucov), read_id);
     for (uint8_t* q = loc; q < e; q++, x++) if (x >= wlo && x < whi) gbase[x] = *q;
     return x;
 }
@@ -96,6 +104,9 @@ __device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int 
 __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64_t n_tiles)
 {
     __shared__ __align__(16) uint8_t sbuf[CW_WARPS][CW_BUF];
+    __shared__ unsigned s_cov[CT_COV];
+    for (int i = threadIdx.x; i < CT_COV; i += CW_THREADS) s_cov[i] = a.cov_tab[i];
+    __syncthreads();
     const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tl = (int64_t)blockIdx.x * CW_WARPS + warp;
     if (tl >= n_tiles) return;
@@ -148,19 +159,44 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
         const bool crossing = sl0 + CW_CHUNK - 1 >= re - 1; // the chunk reaches this read's sentinel
         if (crossing) while (s0 < nvalid && s0 >= lre) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
         const int frs = lrs, fre = lre, fmr = lmr; // the format pass restarts here
-        // pass 1: sizes
-        int size = 0, meta[CW_PER];
+        // pass 1: sizes.  Fast lane: all four slots exist, every bin is inside the tables (position < 10^6, coverage in
+        // [0, 1000)); sentinels ("\n") and the "read i " prefix of a read's first slot are handled on the fast path too.
+        bool               fast = s0 + 3 < nvalid;
+        unsigned long long ek[CW_PER];
+        int                size = 0, meta[CW_PER];
+        if (fast) {
 #pragma unroll
-        for (int k = 0; k < CW_PER; k++) {
-            const int      s = s0 + k;
-            const bool     sentinel = s == lre - 1, neg = cv[k] < 0;
-            const unsigned ucov = neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k];
-            const int      dpos = dec_digits((unsigned)(s - lrs) * reso), dcov = ucov < 100u ? 1 + (int)(ucov > 9u) : dec_digits(ucov);
-            meta[k] = dpos | (dcov << 4);
-            if (s < nvalid) {
-                size += sentinel ? 1 : dpos + dcov + 2 + (int)neg;
-                if (s == lrs) size += 6 + dec_digits(rid0 + (unsigned)lmr);
-                if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); } // the next slot starts the next read
+            for (int k = 0; k < CW_PER; k++) {
+                const int  s = s0 + k;
+                const bool sentinel = s == lre - 1;
+                if (s == lrs) { const unsigned id = rid0 + (unsigned)lmr; fast = fast && id < 100000000u; size += 6 + dec_digits(id); }
+                if (!sentinel) {
+                    const int      kk = s - lrs;
+                    const unsigned c = (unsigned)cv[k];
+                    ek[k] = kk < a.tab_n ? __ldg(a.pos_tab + kk) : 0ull;
+                    fast = fast && (ek[k] >> 56) != 0ull && c < 1000u;
+                    size += (int)(ek[k] >> 56) + 2 + (int)(c > 9u) + (int)(c > 99u);
+                } else {
+                    ek[k] = 0ull;
+                    size += 1;
+                    lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); // the next slot starts the next read
+                }
+            }
+        }
+        if (!fast) {
+            size = 0; lrs = frs; lre = fre; lmr = fmr;
+#pragma unroll
+            for (int k = 0; k < CW_PER; k++) {
+                const int      s = s0 + k;
+                const bool     sentinel = s == lre - 1, neg = cv[k] < 0;
+                const unsigned ucov = neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k];
+                const int      dpos = dec_digits((unsigned)(s - lrs) * reso), dcov = ucov < 100u ? 1 + (int)(ucov > 9u) : dec_digits(ucov);
+                meta[k] = dpos | (dcov << 4);
+                if (s < nvalid) {
+                    size += sentinel ? 1 : dpos + dcov + 2 + (int)neg;
+                    if (s == lrs) size += 6 + dec_digits(rid0 + (unsigned)lmr);
+                    if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); } // the next slot starts the next read
+                }
             }
         }
         const int incl = warp_inclusive_sum(size), ex = incl - size;
@@ -171,15 +207,78 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
             lrs = frs; lre = fre; lmr = fmr;
             if (tot <= a.text_cap) {
                 const int phase = (gl + ro) & 15;
-                uint8_t*  p = wb + phase + ex;
+                if (fast) {
+                    const int o = phase + ex;                    // the lane's text starts at byte o of the warp buffer
+                    unsigned* wp = reinterpret_cast<unsigned*>(wb + (o & ~3));
+                    const int fill0 = o & 3;                     // bytes of the first word that belong to the previous lane
+                    int       fill = fill0;
+                    unsigned  acc = 0;
+                    bool      head = true;                       // the lane's first word has not gone out yet
+                    // appends L <= 12 bytes (first byte in the lowest byte of W0): whole words go out as words, the rest waits in acc
+                    auto append = [&](unsigned W0, unsigned W1, unsigned W2, int L) {
+                        const unsigned s8 = (unsigned)fill * 8u;
+                        const unsigned X0 = acc | (W0 << s8), X1 = __funnelshift_l(W0, W1, s8), X2 = __funnelshift_l(W1, W2, s8),
+                                       X3 = __funnelshift_l(W2, 0u, s8);
+                        const int      total = fill + L, nfull = total >> 2;
+                        if (nfull > 0) {
+                            if (head && fill0) { // only the bytes from fill0 on are this lane's
+                                uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+                                if (fill0 <= 1) bp[1] = (uint8_t)(X0 >> 8);
+                                if (fill0 <= 2) bp[2] = (uint8_t)(X0 >> 16);
+                                bp[3] = (uint8_t)(X0 >> 24);
+                            } else wp[0] = X0;
+                            head = false;
+                        }
+                        if (nfull > 1) wp[1] = X1;
+                        if (nfull > 2) wp[2] = X2;
+                        wp += nfull;
+                        acc = (nfull & 2) ? ((nfull & 1) ? X3 : X2) : ((nfull & 1) ? X1 : X0);
+                        fill = total & 3;
+                    };
 #pragma unroll
-                for (int k = 0; k < CW_PER; k++) {
-                    const int s = s0 + k;
-                    if (s < nvalid) {
-                        const bool sentinel = s == lre - 1, neg = cv[k] < 0;
-                        p = cov_slot_format(p, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso, meta[k] & 15,
-                                            neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], meta[k] >> 4, rid0 + (unsigned)lmr);
-                        if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
+                    for (int k = 0; k < CW_PER; k++) {
+                        const int  s = s0 + k;
+                        const bool sentinel = s == lre - 1;
+                        if (s == lrs) { // "read <id> ": the five letters, then the id's digits and a blank (id < 10^8 on this path)
+                            const unsigned id = rid0 + (unsigned)lmr;
+                            const int      nd = dec_digits(id);
+                            const unsigned hi4 = id / 10000u, A = ascii4(hi4), B = ascii4(id - hi4 * 10000u); // 8 digits, leading zeros included
+                            const unsigned sh = 8u * (unsigned)((8 - nd) & 3);
+                            unsigned       D0, D1;                                                       // the nd digits, first in the lowest byte
+                            if (nd > 4) { D0 = __funnelshift_r(A, B, sh); D1 = B >> sh; } else { D0 = B >> sh; D1 = 0u; }
+                            // a blank after the last digit
+                            if (nd < 4) D0 |= 0x20u << (8 * nd); else if (nd == 4) D1 = 0x20u; else if (nd < 8) D1 |= 0x20u << (8 * (nd - 4));
+                            append(0x64616572u, 0x20u, 0u, 5);
+                            append(D0, D1, nd == 8 ? 0x20u : 0u, nd + 1);
+                        }
+                        if (!sentinel) {
+                            const unsigned long long e = ek[k];
+                            const unsigned c = (unsigned)cv[k], ct = s_cov[c];      // digits + ' ' (2..4 bytes)
+                            const int      aa = (int)(e >> 56), bb = 2 + (int)(c > 9u) + (int)(c > 99u);
+                            const unsigned lo = (unsigned)e, hi = (unsigned)(e >> 32) & 0x00FFFFFFu, sh = (unsigned)(aa & 3) * 8u;
+                            const unsigned c_lo = ct << sh, c_hi = __funnelshift_l(ct, 0u, sh);
+                            if (aa < 4) append(lo | c_lo, c_hi, 0u, aa + bb); else append(lo, hi | c_lo, c_hi, aa + bb);
+                        } else {
+                            append(0x0Au, 0u, 0u, 1);
+                            lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]);
+                        }
+                    }
+                    uint8_t*  bp = reinterpret_cast<uint8_t*>(wp); // the last partial word shares its other bytes with the next lane
+                    const int from = head ? fill0 : 0;
+                    if (fill > 0 && from <= 0) bp[0] = (uint8_t)acc;
+                    if (fill > 1 && from <= 1) bp[1] = (uint8_t)(acc >> 8);
+                    if (fill > 2 && from <= 2) bp[2] = (uint8_t)(acc >> 16);
+                } else {
+                    uint8_t* p = wb + phase + ex;
+#pragma unroll
+                    for (int k = 0; k < CW_PER; k++) {
+                        const int s = s0 + k;
+                        if (s < nvalid) {
+                            const bool sentinel = s == lre - 1, neg = cv[k] < 0;
+                            p = cov_slot_format(p, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso, meta[k] & 15,
+                                                neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], meta[k] >> 4, rid0 + (unsigned)lmr);
+                            if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
+                        }
                     }
                 }
                 __syncwarp();
@@ -197,8 +296,8 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
                     const int s = s0 + k;
                     if (s < nvalid) {
                         const bool sentinel = s == lre - 1, neg = cv[k] < 0;
-                        x = cov_slot_direct(gbase, x, wlo, whi, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso, meta[k] & 15,
-                                            neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], meta[k] >> 4, rid0 + (unsigned)lmr);
+                        x = cov_slot_direct(gbase, x, wlo, whi, s == lrs, sentinel, neg, (unsigned)(s - lrs) * reso,
+                                            neg ? (unsigned)(-(int64_t)cv[k]) : (unsigned)cv[k], rid0 + (unsigned)lmr);
                         if (sentinel) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
                     }
                 }
@@ -223,6 +322,39 @@ void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, 
     if (m > 0) k_cov_tile_index<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(slot_off, m, T, tile_read);
 }
 
+// position text of bin k ("<k*reso>,": at most 6 digits + comma in the low 7 bytes, their count in the top byte; 0 = not
+// representable, take the generic path) and coverage text ("<c> " for c < 1000, first digit in the lowest byte)
+__global__ void __launch_bounds__(256) k_cov_tables(unsigned long long* pos_tab, int n, unsigned reso, unsigned* cov_tab)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const unsigned long long pos = (unsigned long long)k * reso;
+        unsigned long long       e = 0;
+        if (pos < 1000000ull) {
+            unsigned  v = (unsigned)pos;
+            const int nd = dec_digits(v);
+            for (int i = nd - 1; i >= 0; i--) { e |= (unsigned long long)('0' + v % 10u) << (8 * i); v /= 10u; }
+            e |= (unsigned long long)',' << (8 * nd);
+            e |= (unsigned long long)(nd + 1) << 56;
+        }
+        pos_tab[k] = e;
+    }
+    if (k < CT_COV) {
+        unsigned  v = (unsigned)k, t = 0;
+        const int nd = dec_digits(v);
+        if (nd <= 3) {
+            for (int i = nd - 1; i >= 0; i--) { t |= ('0' + v % 10u) << (8 * i); v /= 10u; }
+            t |= (unsigned)' ' << (8 * nd);
+        }
+        cov_tab[k] = t;
+    }
+}
+void launch_cov_tables(unsigned long long* pos_tab, int n, int reso, unsigned* cov_tab, cudaStream_t st)
+{
+    const int cnt = n > CT_COV ? n : CT_COV;
+    k_cov_tables<<<(cnt + 255) / 256, 256, 0, st>>>(pos_tab, n, (unsigned)reso, cov_tab);
+}
+
 int  cov_tiles(int64_t n_slots) { return (int)((n_slots + COV_TILE_SLOTS - 1) / COV_TILE_SLOTS); }
 void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream_t st)
 {
@@ -230,7 +362,13 @@ void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream
     CovEmitArgs a = a_in;
     a.text_cap = CW_CAP;
     if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CW_CAP) a.text_cap = v; } // test knob: force the direct path
-    k_cov_text<<<(unsigned)((n_tiles_launch + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, st>>>(a, n_tiles_launch);
+    static int pad = -1; // experiment knob: unused dynamic shared memory that limits how many text CTAs share an SM with the gather
+    if (pad < 0) {
+        const char* e = getenv("RAFT_B200_CW_PAD");
+        pad = e ? atoi(e) : 0;
+        if (pad > 0) cudaFuncSetAttribute(k_cov_text, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
+    k_cov_text<<<(unsigned)((n_tiles_launch + CW_WARPS - 1) / CW_WARPS), CW_THREADS, (size_t)pad, st>>>(a, n_tiles_launch);
 }
 
 // ================================================================ K5c long_repeats.txt
@@ -634,7 +772,9 @@ void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
 {
     if (a.w1 <= a.w0 || a.G <= 0) return;
     int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
-    int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
+    static int per_sm = 0; // experiment knob: gather CTAs per SM (4 fill the register file)
+    if (!per_sm) { const char* e = getenv("RAFT_B200_FE_CTAS"); per_sm = e && atoi(e) > 0 ? atoi(e) : 4; }
+    int64_t grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
         kern<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);

@@ -223,7 +223,12 @@ struct CovEmitArgs {
     int64_t        tile_first; // first tile of this launch
     const int32_t* tile_read;  // n_tiles+1: read containing the tile's first slot (last entry = m-1 sentinel)
     int            text_cap;   // 32-slot chunks with more text than this take the direct (byte-wise) path
+    const unsigned long long* pos_tab; // text of "<k*reso>," per bin index k < tab_n (launch_cov_tables)
+    int            tab_n;
+    const unsigned* cov_tab;   // text of "<c> " for c < 1000 (COV_TAB_ENTRIES entries)
 };
+constexpr int COV_POS_TAB_ENTRIES = 65536, COV_TAB_ENTRIES = 1024;
+void launch_cov_tables(unsigned long long* pos_tab, int n, int reso, unsigned* cov_tab, cudaStream_t st);
 // tile_read[T] = read whose slots contain slot T*COV_TILE_SLOTS
 void launch_cov_tile_index(const int64_t* slot_off, int64_t m, int64_t n_slots, int32_t* tile_read, cudaStream_t st);
 int  cov_tiles(int64_t n_slots);

@@ -83,6 +83,17 @@ int main(int argc, char* argv[])
     // would join them (README.md:35-36 merges hifiasm's two *.ovlp.paf files before calling raft).
     const char* multi = getenv("RAFT_B200_MULTI_PAF");
     const int   n_paf = (multi && atoi(multi) != 0) ? argc - optind - 1 : 1;
+    // NCCL (sharded runs) writes its debug lines to stdout by default: the reference's stdout lines are part of the drop-in
+    // contract, so they go to stderr unless the user chose a file
+    if (devs.size() > 1) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    // CUDA initialises every visible GPU of the box: expose only the ones this run uses (about 0.2 s per spared device)
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        if (devs.empty()) devs.push_back(dev_env ? atoi(dev_env) : 0);
+        std::string vis;
+        for (size_t k = 0; k < devs.size(); k++) { vis += (k ? "," : "") + std::to_string(devs[k]); devs[k] = (int)k; }
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+    setenv("RAFT_B200_NO_TEARDOWN", "1", 0); // this process ends right after the call: see host_io.cpp
     int         st = devs.size() > 1 ? raftgpu_break_long_reads_mgpu(argv[optind], n_paf, argv + optind + 1, &p, prefix.c_str(), (int)devs.size(),
                                                                      devs.data(), nullptr)
                                      : raftgpu_break_long_reads_multi(argv[optind], n_paf, argv + optind + 1, &p, prefix.c_str(),
@@ -96,5 +107,7 @@ int main(int argc, char* argv[])
     fprintf(stdout, "INFO, %s(), CMD:", __func__);
     for (int i = 0; i < argc; ++i) fprintf(stdout, " %s", argv[i]);
     std::cout << "\n";
-    return 0;
+    std::cout.flush();
+    fflush(stdout);
+    _exit(0); // skip the CUDA runtime's exit-time teardown: the driver reclaims the context with the process
 }

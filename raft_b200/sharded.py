@@ -186,13 +186,18 @@ def bench(a, rank, world, local, log):
     win2 = torch.empty(WINDOW + 64, dtype=torch.uint8, device=dev)
     OUTS = (api.OUT_COVERAGE, api.OUT_LONG_REPEATS, api.OUT_READS_FASTA)
 
+    phase = {}
+
     def step(host=None):
+        import time
+        t0 = time.perf_counter()
         if host is None:
             ctx.set_reads_sharded(ds.n, ds.lengths, ds.name_off, ds.names, b0, b1 - b0, own_off, own_seq)
             st, info = ctx.run_sharded(bounds, ds.paf, ds.paf.numel())
         else:
             ctx.set_reads_sharded(ds.n, host["lengths"], host["name_off"], host["names"], b0, b1 - b0, host["own_off"], host["own_seq"])
             st, info = ctx.run_sharded(bounds, host["paf"], ds.paf.numel())
+        t1 = time.perf_counter()
         nout = 0
         if host is None:  # device windows: text streams and the gather overlap on the library's two emit streams
             for which in OUTS:
@@ -208,6 +213,9 @@ def bench(a, rank, world, local, log):
                 for off in range(0, n, WINDOW):
                     ctx.fetch_into(which, off, dst, min(WINDOW, n - off))
                 nout += n
+        t2 = time.perf_counter()
+        phase["inputs+run_ms"] = (t1 - t0) * 1e3
+        phase["outputs_ms"] = (t2 - t1) * 1e3
         return st, info, nout
 
     def timed(k, host=None):
@@ -271,7 +279,8 @@ def bench(a, rank, world, local, log):
         h2d = sum(int(v.nbytes) for kk, v in host.items() if kk != "out")
         io = comm.all_gather_i64([h2d, nout_e])
         e2e = {"value": info.n_records_total / (ms_e / 1e3), "unit": "overlaps/s", "h2d_bytes_per_step": int(io[:, 0].sum()),
-               "d2h_bytes_per_step": int(io[:, 1].sum()), "ms_per_step": ms_e, "steps": k}
+               "d2h_bytes_per_step": int(io[:, 1].sum()), "ms_per_step": ms_e, "steps": k,
+               "host_wall_rank0_last_step": {kk: round(v, 1) for kk, v in phase.items() if kk.endswith("_ms")}}
         dig_e = all_digests(info_e)
         checks.append({"what": "e2e run (pinned host inputs through the C ABI on every rank) vs the device-resident run", "vs": "n-gpu device-resident",
                        "scale": a.scale, "identical": dig_e == dig})

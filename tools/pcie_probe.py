@@ -3,6 +3,8 @@
 Prints one JSON line: H2D alone, D2H alone, and both directions at once (two streams), GB/s.
 """
 import json
+import sys
+
 import torch
 
 
@@ -21,6 +23,8 @@ def rate(fn, nbytes, reps=3):
 
 
 def main():
+    if "--device" in sys.argv:
+        torch.cuda.set_device(int(sys.argv[sys.argv.index("--device") + 1]))
     n = 4 << 30
     h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -41,6 +45,7 @@ def main():
         cur.wait_stream(s1); cur.wait_stream(s2)
 
     out["bidir_each_gbs"] = rate(both, n)
+    out["device"] = torch.cuda.current_device()
     print(json.dumps(out))
 
 
