@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libraft_b200.so")
+LIB_PATH = os.environ.get("RAFT_B200_LIB") or os.path.join(HERE, "libraft_b200.so")  # the variable selects an experimental build
 
 # every symbol include/raft_b200.h declares
 SYMBOLS = [

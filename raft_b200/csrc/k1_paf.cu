@@ -270,11 +270,10 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k_paf_tokenize(PafTokArgs a)
 
     // ---- newline / tab masks: one 16-byte group per lane, two lanes make one 32-bit word
     const uint4* t16 = reinterpret_cast<const uint4*>(s.text);
-    for (int g = tid; g < K1_STAGE / 16; g += K1_THREADS) { // 1088 groups = 6 rounds of 160 + four full warps
-        uint4    v = t16[g];
-        unsigned mn = eq_mask16(v, 0x0A0A0A0Au), mt = eq_mask16(v, 0x09090909u);
-        unsigned pn = __shfl_down_sync(FULL, mn, 1), pt = __shfl_down_sync(FULL, mt, 1);
-        if (!(lane & 1)) { s.nl[g >> 1] = mn | (pn << 16); s.tab[g >> 1] = mt | (pt << 16); }
+    for (int w = tid; w < K1_WORDS; w += K1_THREADS) {
+        const uint4 v0 = t16[2 * w], v1 = t16[2 * w + 1];
+        s.nl[w] = eq_mask16(v0, 0x0A0A0A0Au) | (eq_mask16(v1, 0x0A0A0A0Au) << 16);
+        s.tab[w] = eq_mask16(v0, 0x09090909u) | (eq_mask16(v1, 0x09090909u) << 16);
     }
     if (tid == 0) { s.nl[K1_WORDS] = 0xFFFFFFFFu; s.tab[K1_WORDS] = 0xFFFFFFFFu; s.n_invalid = 0; }
     __syncthreads();

@@ -159,12 +159,26 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
         const bool crossing = sl0 + CW_CHUNK - 1 >= re - 1; // the chunk reaches this read's sentinel
         if (crossing) while (s0 < nvalid && s0 >= lre) { lmr++; lrs = lre; lre = rel(a.slot_off[r + lmr + 1]); }
         const int frs = lrs, fre = lre, fmr = lmr; // the format pass restarts here
-        // pass 1: sizes.  Fast lane: all four slots exist, every bin is inside the tables (position < 10^6, coverage in
-        // [0, 1000)); sentinels ("\n") and the "read i " prefix of a read's first slot are handled on the fast path too.
+        // pass 1: sizes.  Three kinds of lanes:
+        //  plain    -- four ordinary bins of one read (not its first slot, none its sentinel), all inside the tables (position
+        //              < 10^6, coverage in [0, 1000)): the specialised table path;
+        //  boundary -- all four slots exist and are inside the tables, but some are sentinels ("\n") or open a read
+        //              ("read <id> " in front): the same table path through a general append;
+        //  generic  -- everything else (table misses, the ragged end of the last tile): digit by digit.
+        const int          k0 = s0 - lrs;
+        const bool         plain = s0 + 3 < nvalid && k0 > 0 && s0 + 3 < lre - 1 && k0 + 3 < a.tab_n;
         bool               fast = s0 + 3 < nvalid;
         unsigned long long ek[CW_PER];
         int                size = 0, meta[CW_PER];
-        if (fast) {
+        if (plain) {
+#pragma unroll
+            for (int k = 0; k < CW_PER; k++) {
+                ek[k] = __ldg(a.pos_tab + k0 + k);
+                const unsigned c = (unsigned)cv[k];
+                fast = fast && (ek[k] >> 56) != 0ull && c < 1000u;
+                size += (int)(ek[k] >> 56) + 2 + (int)(c > 9u) + (int)(c > 99u);
+            }
+        } else if (fast) {
 #pragma unroll
             for (int k = 0; k < CW_PER; k++) {
                 const int  s = s0 + k;
@@ -207,7 +221,40 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
             lrs = frs; lre = fre; lmr = fmr;
             if (tot <= a.text_cap) {
                 const int phase = (gl + ro) & 15;
-                if (fast) {
+                if (fast && plain) {
+                    const int o = phase + ex;                    // the lane's text starts at byte o of the warp buffer
+                    unsigned* wp = reinterpret_cast<unsigned*>(wb + (o & ~3));
+                    int       fill = o & 3;                      // bytes of the first word that belong to the previous lane
+                    unsigned  acc = 0;
+#pragma unroll
+                    for (int k = 0; k < CW_PER; k++) {
+                        const unsigned long long e = ek[k];
+                        const unsigned c = (unsigned)cv[k], ct = s_cov[c];      // digits + ' ' (2..4 bytes)
+                        const int      aa = (int)(e >> 56), bb = 2 + (int)(c > 9u) + (int)(c > 99u);
+                        const unsigned lo = (unsigned)e, hi = (unsigned)(e >> 32) & 0x00FFFFFFu, sh = (unsigned)(aa & 3) * 8u;
+                        const unsigned c_lo = ct << sh, c_hi = __funnelshift_l(ct, 0u, sh);
+                        unsigned       W0, W1, W2;                              // the slot's text, first byte in the lowest byte of W0
+                        if (aa < 4) { W0 = lo | c_lo; W1 = c_hi; W2 = 0u; } else { W0 = lo; W1 = hi | c_lo; W2 = c_hi; }
+                        const unsigned s8 = (unsigned)fill * 8u;
+                        const unsigned X0 = acc | (W0 << s8), X1 = __funnelshift_l(W0, W1, s8), X2 = __funnelshift_l(W1, W2, s8),
+                                       X3 = __funnelshift_l(W2, 0u, s8);
+                        const int      total = fill + aa + bb, nfull = total >> 2;
+                        if (k == 0) { // a bin has >= 4 bytes: the first word always completes; its leading `fill` bytes are not this lane's
+                            uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+                            if (fill == 0) wp[0] = X0;
+                            else { if (fill <= 1) bp[1] = (uint8_t)(X0 >> 8); if (fill <= 2) bp[2] = (uint8_t)(X0 >> 16); bp[3] = (uint8_t)(X0 >> 24); }
+                        } else if (nfull > 0) wp[0] = X0;
+                        if (nfull > 1) wp[1] = X1;
+                        if (nfull > 2) wp[2] = X2;
+                        wp += nfull;
+                        acc = (nfull & 2) ? ((nfull & 1) ? X3 : X2) : ((nfull & 1) ? X1 : X0);
+                        fill = total & 3;
+                    }
+                    uint8_t* bp = reinterpret_cast<uint8_t*>(wp); // the last partial word shares its other bytes with the next lane
+                    if (fill > 0) bp[0] = (uint8_t)acc;
+                    if (fill > 1) bp[1] = (uint8_t)(acc >> 8);
+                    if (fill > 2) bp[2] = (uint8_t)(acc >> 16);
+                } else if (fast) {
                     const int o = phase + ex;                    // the lane's text starts at byte o of the warp buffer
                     unsigned* wp = reinterpret_cast<unsigned*>(wb + (o & ~3));
                     const int fill0 = o & 3;                     // bytes of the first word that belong to the previous lane
