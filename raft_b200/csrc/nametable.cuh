@@ -50,12 +50,28 @@ struct NameHasher {
     }
 };
 
+// Same value as NameHasher fed byte by byte, from global memory four bytes at a time: aligned 32-bit loads of the words that
+// hold the name (never a word past its last byte) and a funnel shift for names that do not start on a word boundary.
 __device__ __forceinline__ unsigned long long hash_name_global(const uint8_t* s, int64_t len, unsigned long long seed)
 {
     NameHasher hs;
     hs.init(seed);
-    for (int64_t i = 0; i < len; i++) hs.add(s[i]);
-    return hs.finish();
+    const unsigned  mis = (unsigned)((uintptr_t)s & 3u), sh = mis * 8u;
+    const unsigned* q = reinterpret_cast<const unsigned*>(s - mis);
+    const int64_t   nw = ((int64_t)mis + len + 3) >> 2; // aligned words covering [s, s + len)
+    unsigned        lo = nw > 0 ? q[0] : 0u;
+    int64_t         k = 0, wi = 0;
+    for (; k + 4 <= len; k += 4) {
+        const unsigned hi = wi + 1 < nw ? q[wi + 1] : 0u;
+        hs.word(__funnelshift_r(lo, hi, sh));
+        lo = hi; wi++;
+    }
+    const int rem = (int)(len - k);
+    if (rem) {
+        const unsigned hi = wi + 1 < nw ? q[wi + 1] : 0u;
+        hs.word(__funnelshift_r(lo, hi, sh) & ((1u << (8 * rem)) - 1u));
+    }
+    return name_hash_finish(hs.a, hs.b, (unsigned)len);
 }
 
 __device__ __forceinline__ int nametable_find(const NameTable& t, unsigned long long key)

@@ -196,7 +196,9 @@ def bench(a, rank, world, local, log):
             st, info = ctx.run_sharded(bounds, ds.paf, ds.paf.numel())
         else:
             ctx.set_reads_sharded(ds.n, host["lengths"], host["name_off"], host["names"], b0, b1 - b0, host["own_off"], host["own_seq"])
+            phase["set_reads_ms"] = (time.perf_counter() - t0) * 1e3
             st, info = ctx.run_sharded(bounds, host["paf"], ds.paf.numel())
+            phase["tokenize_device_ms"] = st.ms_tokenize
         t1 = time.perf_counter()
         nout = 0
         if host is None:  # device windows: text streams and the gather overlap on the library's two emit streams

@@ -149,8 +149,9 @@ def test_cli_on_several_gpus(ndev, fastq):
         for tag, env in (("one", dict(os.environ, RAFT_B200_MULTI_PAF="1")),
                          ("many", dict(os.environ, RAFT_B200_MULTI_PAF="1", RAFT_B200_DEVICES=",".join(str(k) for k in range(ndev))))):
             r = subprocess.run([exe] + ds.args + ["-o", os.path.join(d, tag), os.path.join(d, "r.fa"), os.path.join(d, "a.paf"), os.path.join(d, "b.paf")],
-                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=env)
-            assert r.returncode == 0, r.stdout.decode()
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+            assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+            # stdout alone is compared: NCCL's version banner and debug lines must have gone to stderr
             outs[tag] = [l for l in r.stdout.decode().splitlines() if "program completed" not in l and "CMD:" not in l]
             for suf, data in zip(("coverage.txt", "long_repeats.txt", "long_repeats.bed", "reads.fasta"), (ref.cov_txt, ref.rep_txt, ref.bed_txt, ref.fasta)):
                 assert open(os.path.join(d, f"{tag}.{suf}"), "rb").read() == data, (tag, suf)
