@@ -680,8 +680,13 @@ extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf
     sh.ctx.assign(P, nullptr); sh.status.assign(P, 0); sh.n_local.assign(P, 0); sh.name_bytes.assign(P, 0);
     sh.info.assign(P, raftgpu_shard_info{}); sh.stats.assign(P, raftgpu_stats{}); sh.paf_seg.assign(P, {});
     auto destroy_all = [&] { for (auto& c : sh.ctx) if (c) { raftgpu_destroy(c); c = nullptr; } };
-    for (int r = 0; r < P; r++)
-        if ((st = raftgpu_create(p, devices[r], &sh.ctx[r]))) { fprintf(stderr, "raft_b200: device %d: %s\n", devices[r], raftgpu_strerror(st)); destroy_all(); return st; }
+    {   // one CUDA context per device: created side by side (each costs some tenths of a second)
+        std::vector<std::thread> mk;
+        for (int r = 0; r < P; r++) mk.emplace_back([&, r] { sh.status[r] = raftgpu_create(p, devices[r], &sh.ctx[r]); });
+        for (auto& t : mk) t.join();
+        for (int r = 0; r < P; r++)
+            if ((st = sh.status[r])) { fprintf(stderr, "raft_b200: device %d: %s\n", devices[r], raftgpu_strerror(st)); destroy_all(); return st; }
+    }
     if ((st = raftgpu_comm_unique_id(sh.comm_id))) { destroy_all(); return st; }
 
     // ---- how the inputs are cut.  Reads: plain FASTA is cut into P byte ranges at record starts ('>' opening a line), each

@@ -293,12 +293,27 @@ __device__ __forceinline__ int owner_of(const int64_t* __restrict__ bounds, int 
     return lo;
 }
 
+// Shared-memory counters per destination are hit by every endpoint of a block: with 2..64 destinations that is a handful of
+// addresses under 256 threads.  The lanes of a warp that go to the same destination are therefore grouped first
+// (__match_any_sync): one atomic per group, the lanes take consecutive positions behind its result.
+// All 32 lanes call it; inactive lanes pass dest = -1.  Returns this lane's position (old value + rank in its group).
+__device__ __forceinline__ unsigned warp_grouped_add(unsigned* counters, int dest)
+{
+    const unsigned grp = __match_any_sync(FULL, dest);
+    const int      leader = __ffs(grp) - 1;
+    unsigned       old = 0;
+    if (dest >= 0 && lane_id() == leader) old = atomicAdd(&counters[dest], (unsigned)__popc(grp));
+    old = __shfl_sync(FULL, old, leader);
+    return old + (unsigned)__popc(grp & ((1u << lane_id()) - 1u));
+}
+
 // Two-pass packing straight from the records (used when the collected list of k_route_collect overflowed): every block
 // counts its chunk's endpoints per destination, reserves a range per destination, then writes.
 __global__ void __launch_bounds__(256) k_route_pack(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
                                                     int32_t* sendbuf)
 {
-    extern __shared__ unsigned long long s_cnt[]; // nranks block-local counts, then nranks block bases
+    extern __shared__ unsigned long long s_base[]; // nranks reserved bases, then nranks 32-bit counts / cursors
+    unsigned*  s_cnt = reinterpret_cast<unsigned*>(s_base + nranks);
     const bool sym = *a.sym_flag != 0;
     for (int r = threadIdx.x; r < nranks; r += blockDim.x) s_cnt[r] = 0;
     __syncthreads();
@@ -307,29 +322,39 @@ __global__ void __launch_bounds__(256) k_route_pack(ScatterArgs a, int nranks, c
     int64_t k0 = (int64_t)blockIdx.x * per, k1 = k0 + per < a.n_rec ? k0 + per : a.n_rec;
     // endpoints of reads this rank owns never leave it (raftgpu_accumulate_local scatters them directly)
     const int64_t own_lo = a.own_first, own_hi = a.own_first + a.own_count;
+    const int64_t kend = k0 + ((k1 - k0 + blockDim.x - 1) / blockDim.x) * blockDim.x; // whole warps walk the chunk together
     // pass 1: count
-    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-        int q = a.qid[k], t = a.tid[k];
-        if (q < own_lo || q >= own_hi) atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull);
-        if (!sym && t != q && (t < own_lo || t >= own_hi)) atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull);
+    for (int64_t k = k0 + threadIdx.x; k < kend; k += blockDim.x) {
+        int dq = -1, dt = -1;
+        if (k < k1) {
+            const int q = a.qid[k], t = a.tid[k];
+            if (q < own_lo || q >= own_hi) dq = owner_of(bounds, nranks, q);
+            if (!sym && t != q && (t < own_lo || t >= own_hi)) dt = owner_of(bounds, nranks, t);
+        }
+        warp_grouped_add(s_cnt, dq);
+        warp_grouped_add(s_cnt, dt);
     }
     __syncthreads();
     // pass 2: reserve a range per destination, then write
     for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
-        s_cnt[nranks + r] = s_cnt[r] ? atomicAdd(&counters[r], s_cnt[r]) : 0ull;
+        s_base[r] = s_cnt[r] ? atomicAdd(&counters[r], (unsigned long long)s_cnt[r]) : 0ull;
         s_cnt[r] = 0;
     }
     __syncthreads();
-    for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-        int q = a.qid[k], t = a.tid[k];
-        if (q < own_lo || q >= own_hi) {
-            int                d = owner_of(bounds, nranks, q);
-            unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
+    for (int64_t k = k0 + threadIdx.x; k < kend; k += blockDim.x) {
+        int dq = -1, dt = -1, q = 0, t = 0;
+        if (k < k1) {
+            q = a.qid[k]; t = a.tid[k];
+            if (q < own_lo || q >= own_hi) dq = owner_of(bounds, nranks, q);
+            if (!sym && t != q && (t < own_lo || t >= own_hi)) dt = owner_of(bounds, nranks, t);
+        }
+        const unsigned pq = warp_grouped_add(s_cnt, dq), pt = warp_grouped_add(s_cnt, dt);
+        if (dq >= 0) {
+            const unsigned long long slot = s_base[dq] + pq;
             sendbuf[3 * slot] = q; sendbuf[3 * slot + 1] = a.qs[k]; sendbuf[3 * slot + 2] = a.qe[k];
         }
-        if (!sym && t != q && (t < own_lo || t >= own_hi)) {
-            int                d = owner_of(bounds, nranks, t);
-            unsigned long long slot = s_cnt[nranks + d] + atomicAdd(&s_cnt[d], 1ull);
+        if (dt >= 0) {
+            const unsigned long long slot = s_base[dt] + pt;
             sendbuf[3 * slot] = t; sendbuf[3 * slot + 1] = a.ts[k]; sendbuf[3 * slot + 2] = a.te[k];
         }
     }
@@ -341,41 +366,56 @@ __global__ void __launch_bounds__(256) k_route_pack(ScatterArgs a, int nranks, c
 __global__ void __launch_bounds__(256) k_route_collect(ScatterArgs a, int nranks, const int64_t* __restrict__ bounds, unsigned long long* counters,
                                                        int4* list, unsigned long long* list_n, unsigned long long cap)
 {
-    extern __shared__ unsigned long long s_cnt[]; // nranks block-local counts, then [nranks] = block total / cursor, [nranks+1] = base
+    extern __shared__ unsigned long long s_base[]; // [0] = base of this block's range in the list, then nranks + 1 32-bit counters
+    unsigned*  s_cnt = reinterpret_cast<unsigned*>(s_base + 1); // [0..nranks) per destination, [nranks] = block total / cursor
     const bool sym = *a.sym_flag != 0;
-    for (int r = threadIdx.x; r < nranks + 2; r += blockDim.x) s_cnt[r] = 0;
+    for (int r = threadIdx.x; r < nranks + 1; r += blockDim.x) s_cnt[r] = 0;
     __syncthreads();
     // a block owns a contiguous chunk of records (a multiple of 1024, so 128-bit loads of the id columns stay aligned)
     const int64_t per = (((a.n_rec + gridDim.x - 1) / gridDim.x) + 1023) & ~(int64_t)1023;
     const int64_t k0 = (int64_t)blockIdx.x * per, k1 = k0 + per < a.n_rec ? k0 + per : a.n_rec;
     const int64_t own_lo = a.own_first, own_hi = a.own_first + a.own_count;
-    auto count_one = [&](int q, int t) {
-        if (q < own_lo || q >= own_hi) { atomicAdd(&s_cnt[owner_of(bounds, nranks, q)], 1ull); atomicAdd(&s_cnt[nranks], 1ull); }
-        if (!sym && t != q && (t < own_lo || t >= own_hi)) { atomicAdd(&s_cnt[owner_of(bounds, nranks, t)], 1ull); atomicAdd(&s_cnt[nranks], 1ull); }
+    unsigned      mine = 0; // endpoints this thread saw (summed per warp, one atomic per warp at the end)
+    auto count_one = [&](int q, int t, bool real) { // all lanes of the warp call it together; !real: padding behind the chunk
+        int dq = -1, dt = -1;
+        if (real && (q < own_lo || q >= own_hi)) dq = owner_of(bounds, nranks, q);
+        if (real && !sym && t != q && (t < own_lo || t >= own_hi)) dt = owner_of(bounds, nranks, t);
+        const unsigned any = __ballot_sync(FULL, dq >= 0 || dt >= 0);
+        if (!any) return; // the usual case with query-grouped symmetric PAF: nothing leaves the rank
+        warp_grouped_add(s_cnt, dq);
+        warp_grouped_add(s_cnt, dt);
+        mine += (unsigned)(dq >= 0) + (unsigned)(dt >= 0);
     };
-    for (int64_t k = k0 + 4 * (int64_t)threadIdx.x; k < k1; k += 4 * (int64_t)blockDim.x) {
+    const int64_t step = 4 * (int64_t)blockDim.x;
+    const int64_t kend = k0 + ((k1 - k0 + step - 1) / step) * step;
+    for (int64_t k = k0 + 4 * (int64_t)threadIdx.x; k < kend; k += step) {
+        int4 q4 = make_int4(0, 0, 0, 0), t4 = q4;
         if (k + 4 <= k1) { // four records per thread and iteration: two 128-bit loads in flight
-            const int4 q4 = *reinterpret_cast<const int4*>(a.qid + k), t4 = *reinterpret_cast<const int4*>(a.tid + k);
-            count_one(q4.x, t4.x); count_one(q4.y, t4.y); count_one(q4.z, t4.z); count_one(q4.w, t4.w);
+            q4 = *reinterpret_cast<const int4*>(a.qid + k); t4 = *reinterpret_cast<const int4*>(a.tid + k);
         } else {
-            for (int64_t j = k; j < k1; j++) count_one(a.qid[j], a.tid[j]);
+            if (k < k1) { q4.x = a.qid[k]; t4.x = a.tid[k]; }
+            if (k + 1 < k1) { q4.y = a.qid[k + 1]; t4.y = a.tid[k + 1]; }
+            if (k + 2 < k1) { q4.z = a.qid[k + 2]; t4.z = a.tid[k + 2]; }
         }
+        count_one(q4.x, t4.x, k < k1); count_one(q4.y, t4.y, k + 1 < k1); count_one(q4.z, t4.z, k + 2 < k1); count_one(q4.w, t4.w, k + 3 < k1);
     }
+    mine = warp_sum(mine);
+    if (lane_id() == 0 && mine) atomicAdd(&s_cnt[nranks], mine);
     __syncthreads();
-    const unsigned long long total = s_cnt[nranks];
+    const unsigned total = s_cnt[nranks];
     if (total == 0) return;
     for (int r = threadIdx.x; r < nranks; r += blockDim.x)
-        if (s_cnt[r]) atomicAdd(&counters[r], s_cnt[r]);
-    if (threadIdx.x == 0) { s_cnt[nranks + 1] = atomicAdd(list_n, total); s_cnt[nranks] = 0; }
+        if (s_cnt[r]) atomicAdd(&counters[r], (unsigned long long)s_cnt[r]);
+    if (threadIdx.x == 0) { s_base[0] = atomicAdd(list_n, (unsigned long long)total); s_cnt[nranks] = 0; }
     __syncthreads();
-    const unsigned long long base = s_cnt[nranks + 1];
+    const unsigned long long base = s_base[0];
     if (base + total > cap) return; // the list cannot hold this block's endpoints: the caller falls back to the two-pass packing
     for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
         int q = a.qid[k], t = a.tid[k];
         if (q < own_lo || q >= own_hi)
-            list[base + atomicAdd(&s_cnt[nranks], 1ull)] = make_int4(q, a.qs[k], a.qe[k], owner_of(bounds, nranks, q));
+            list[base + atomicAdd(&s_cnt[nranks], 1u)] = make_int4(q, a.qs[k], a.qe[k], owner_of(bounds, nranks, q));
         if (!sym && t != q && (t < own_lo || t >= own_hi))
-            list[base + atomicAdd(&s_cnt[nranks], 1ull)] = make_int4(t, a.ts[k], a.te[k], owner_of(bounds, nranks, t));
+            list[base + atomicAdd(&s_cnt[nranks], 1u)] = make_int4(t, a.ts[k], a.te[k], owner_of(bounds, nranks, t));
     }
 }
 // buckets the collected endpoints by destination: cursors[d] = first free endpoint slot of destination d in sendbuf
@@ -392,7 +432,7 @@ void launch_route_collect(const ScatterArgs& a, int nranks, const int64_t* bound
                           unsigned long long* list_n, unsigned long long cap, cudaStream_t st)
 {
     if (a.n_rec <= 0) return;
-    k_route_collect<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * (nranks + 2), st>>>(a, nranks, bounds, counts, list, list_n, cap);
+    k_route_collect<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) + sizeof(unsigned) * (nranks + 2), st>>>(a, nranks, bounds, counts, list, list_n, cap);
 }
 void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
 {
@@ -401,7 +441,7 @@ void launch_route_pack_list(const int4* list, int64_t n, unsigned long long* cur
 void launch_route_pack(const ScatterArgs& a, int nranks, const int64_t* bounds, unsigned long long* cursors, int32_t* sendbuf, cudaStream_t st)
 {
     if (a.n_rec <= 0) return;
-    k_route_pack<<<route_blocks(a.n_rec), 256, sizeof(unsigned long long) * 2 * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
+    k_route_pack<<<route_blocks(a.n_rec), 256, (sizeof(unsigned long long) + sizeof(unsigned)) * nranks, st>>>(a, nranks, bounds, cursors, sendbuf);
 }
 
 __global__ void k_pick_rec0(const int* __restrict__ gathered, int nranks, int rank, int* rec0)

@@ -13,7 +13,7 @@ run C1 --config C1
 run C4 --config C4
 run C5 --config C5
 run C2asym --config C2 --asymmetric
-run C5asym --config C5 --asymmetric
+[ "$N" = 1 ] && run C5asym --config C5 --asymmetric
 run C2 --config C2
 python - "$TAG" "$N" <<'PY'
 import json, sys, glob
