@@ -27,11 +27,17 @@ namespace raftk {
 // shared buffer laid out at the 16-byte phase of its destination, then aligned 128-bit stores.  No block-level
 // barrier and no per-thread search: the read a slot belongs to is warp-uniform state that only moves when a chunk
 // reaches the end of the current read.
+#ifndef CW_PER_N
+#define CW_PER_N 4
+#endif
+#ifndef CW_MINB
+#define CW_MINB 4
+#endif
 constexpr int CW_WARPS = 8;
 constexpr int CW_THREADS = CW_WARPS * 32;
-constexpr int CW_PER = 4;             // slots per lane per chunk
+constexpr int CW_PER = CW_PER_N;      // slots per lane per chunk
 constexpr int CW_CHUNK = 32 * CW_PER;
-constexpr int CW_BUF = 2048;          // per-warp text buffer
+constexpr int CW_BUF = 512 * CW_PER;  // per-warp text buffer
 constexpr int CW_CAP = CW_BUF - 16;   // chunks with more text (tiny reads: many "read i " prefixes) take the direct path
 constexpr int CW_MAX_SLOT_BYTES = 40; // "read 2147483647 " (16) + "2147483647,-2147483648 " (23)
 // Fast lanes (all four slots are ordinary bins of one read): the text of a bin is   <k*reso> ',' <cov> ' '   and both halves
@@ -101,7 +107,7 @@ __device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int 
     return x;
 }
 
-__global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64_t n_tiles)
+__global__ void __launch_bounds__(CW_THREADS, CW_MINB) k_cov_text(CovEmitArgs a, int64_t n_tiles)
 {
     __shared__ __align__(16) uint8_t sbuf[CW_WARPS][CW_BUF];
     __shared__ unsigned s_cov[CT_COV];
@@ -166,8 +172,8 @@ __global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64
         //              ("read <id> " in front): the same table path through a general append;
         //  generic  -- everything else (table misses, the ragged end of the last tile): digit by digit.
         const int          k0 = s0 - lrs;
-        const bool         plain = s0 + 3 < nvalid && k0 > 0 && s0 + 3 < lre - 1 && k0 + 3 < a.tab_n;
-        bool               fast = s0 + 3 < nvalid;
+        const bool         plain = s0 + CW_PER - 1 < nvalid && k0 > 0 && s0 + CW_PER - 1 < lre - 1 && k0 + CW_PER - 1 < a.tab_n;
+        bool               fast = s0 + CW_PER - 1 < nvalid;
         unsigned long long ek[CW_PER];
         int                size = 0, meta[CW_PER];
         if (plain) {

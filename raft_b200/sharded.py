@@ -2,14 +2,19 @@
 
 The reference has no distributed mode; the path shards naturally because the
 coverage of a read depends only on the records that name it (repeat.hpp:48-58) and everything after
-coverage is per read.  Protocol per rank (`run_rank`):
+coverage is per read.
+
+The sharded run itself lives in the library (raftgpu_run_sharded, csrc/api.cu: NCCL collectives and
+ncclSend/ncclRecv on the context's stream); `bench` below drives it under torchrun.  `run_rank` is the same
+protocol spelled out over the caller-driven building blocks and torch.distributed, kept for the CPU test of the
+protocol (gloo, numpy stand-in engine) and for boxes with a single GPU, where NCCL cannot put two ranks on one device:
 
   1. every rank tokenises its byte range of the PAF (split at newlines) against the full name table;
   2. record 0 of the whole file (chop.hpp:171-184 compares every later record with it) is taken from
      the first rank that has a record and broadcast; the symmetric flag is the max over ranks;
   3. intervals on reads the rank owns are scattered locally; every other contributing interval becomes
      a 12-byte endpoint (global read id, start, end) for the rank that owns the read: counts
-     all-to-all, then ONE data all-to-all (NCCL over NVLink);
+     all-to-all, then ONE data all-to-all;
   4. each rank accumulates the endpoints it received, finalises its own reads, and the global
      `read=` numbering is fixed by an all-gather of fragment counts (chop.hpp:195,266,319).
 
