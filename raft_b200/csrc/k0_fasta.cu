@@ -12,7 +12,8 @@
 //   * "am I inside a header line at the start of the tile" is a last-writer scan over tiles, resolved with a
 //     look-back: a tile that contains a newline knows its own carry-out and publishes it immediately;
 //   * kept-byte and record counts get their global offsets from two decoupled look-backs;
-//   * kept bytes are compacted in shared memory at the destination's 16-byte phase and stored with 128-bit writes.
+//   * kept bytes come in long runs (whole lines): warps copy run pieces straight from the staged tile to the arena with
+//     realigning shared-memory loads and aligned 128-bit stores.
 // Outputs: the arena, and per record its file position and its offset in the arena.  Names are cut out by two
 // tiny per-record kernels afterwards.
 //
@@ -37,7 +38,6 @@ constexpr int F0_PIECE = 1024;
 
 struct __align__(16) F0Smem {
     uint8_t  text[F0_TILE + 16];
-    uint8_t  out[F0_TILE + 32];
     unsigned nl[F0_WORDS + 1];  // (+1: all-ones sentinel)
     unsigned hdr[F0_WORDS];     // byte belongs to a header line (including its newline)
     uint64_t bar;
@@ -90,7 +90,7 @@ __device__ __forceinline__ int f0_resolve_carry(const uint64_t* status, int tile
 }
 
 template <bool FQ>
-__global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a)
+__global__ void __launch_bounds__(F0_THREADS, 8) k_fasta_tokenize(FastaTokArgs a)
 {
     extern __shared__ __align__(16) uint8_t f0_raw[];
     F0Smem& s = *reinterpret_cast<F0Smem*>(f0_raw);
@@ -269,11 +269,9 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
             kept_before += __popc(keep[i]);
         }
     }
-    // ---- compact the kept bytes at the destination's 16-byte phase, then aligned 128-bit stores.
-    // Kept bytes come in long runs (whole lines): list the runs (pieces of <= 1 KiB) and let each warp copy pieces with
+    // ---- kept bytes come in long runs (whole lines): list the runs (pieces of <= 1 KiB) and let each warp copy pieces with
     // lane-consecutive bytes; per-thread copying of its own 64 bytes would be a 16-way shared-memory bank conflict.
     const uintptr_t gdst0 = (uintptr_t)a.seq_out + (uintptr_t)base_keep;
-    const int       phase = (int)(gdst0 & 15);
     if (tid == 0) s.n_runs = 0;
     // summary of the dropped-byte mask (one ballot per 32 words) so that the end of a long run is found in a few steps
     for (int w = tid; w < F0_WORDS; w += F0_THREADS) {
@@ -313,23 +311,26 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
         }
     }
     __syncthreads();
+    uint8_t* const gout = reinterpret_cast<uint8_t*>(gdst0); // arena position of the tile's first kept byte
     if (s.n_runs <= F0_RUNCAP) {
+        // every warp copies pieces of <= 1 KiB straight from the staged text to the arena: bytes up to the destination's
+        // first 16-byte boundary, then aligned 128-bit streaming stores fed by realigning shared-memory loads, then bytes
         const int nr = s.n_runs, warp = warp_id();
         for (int r = warp; r < nr; r += F0_THREADS / 32) {
             const uint8_t* src = s.text + s.run_src[r];
-            uint8_t*       o = s.out + phase + s.run_dst[r];
+            uint8_t*       o = gout + s.run_dst[r];
             const int      n = s.run_len[r];
-            // realigning copy: bytes up to the first 16-byte boundary of the destination, 16-byte chunks, bytes
-            int head = (int)((16 - (smem_u32(o) & 15)) & 15);
+            int head = (int)((16 - ((uintptr_t)o & 15)) & 15);
             if (head > n) head = n;
             if (lane < head) o[lane] = src[lane];
             const int nbody = (n - head) >> 4;
-            for (int c = lane; c < nbody; c += 32) *reinterpret_cast<uint4*>(o + head + (c << 4)) = lds_unaligned16(src + head + (c << 4));
+            uint4*    o16 = reinterpret_cast<uint4*>(o + head);
+            for (int c = lane; c < nbody; c += 32) stg_stream(o16 + c, lds_unaligned16(src + head + (c << 4)));
             const int done = head + (nbody << 4);
             if (done + lane < n) o[done + lane] = src[done + lane];
         }
     } else { // pathological tile (thousands of tiny lines): every thread copies the kept bytes of its own words
-        uint8_t* o = s.out + phase + ex_keep;
+        uint8_t* o = gout + ex_keep;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             unsigned       m = keep[i];
@@ -337,15 +338,6 @@ __global__ void __launch_bounds__(F0_THREADS, 5) k_fasta_tokenize(FastaTokArgs a
             while (m) { int bit = __ffs(m) - 1; m &= m - 1; *o++ = src[bit]; }
         }
     }
-    __syncthreads();
-    const uintptr_t ga1 = gdst0 + (uintptr_t)tot_keep;
-    uintptr_t       fa = (gdst0 + 15) & ~(uintptr_t)15, la = ga1 & ~(uintptr_t)15;
-    if (fa > la) { fa = ga1; la = ga1; }
-    const uint8_t* sb = s.out + phase;
-    for (uintptr_t x = gdst0 + tid; x < fa; x += F0_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
-    for (uintptr_t x = fa + (uintptr_t)tid * 16; x < la; x += (uintptr_t)F0_THREADS * 16)
-        stg_stream(reinterpret_cast<uint4*>(x), *reinterpret_cast<const uint4*>(sb + (x - gdst0)));
-    for (uintptr_t x = la + tid; x < ga1; x += F0_THREADS) *reinterpret_cast<uint8_t*>(x) = sb[x - gdst0];
 }
 
 int         fasta_tokenize_tiles(int64_t nbytes) { return (int)((nbytes + F0_TILE - 1) / F0_TILE); }

@@ -61,5 +61,5 @@ def test_no_cpu_fallback():
         api.Context(api.AlgoParams(est_cov=30))
     assert ei.value.status == -8                                          # RAFTGPU_E_CUDA: no usable sm_100 device
     with pytest.raises(api.RaftError):
-        api.break_long_reads(os.path.join(ROOT, "tests", "golden", "edge", "in.r.fa"), os.path.join(ROOT, "tests", "golden", "edge", "in.asym.paf"),
+        api.break_long_reads(os.path.join(ROOT, "tests", "golden", "edge", "in.fa"), os.path.join(ROOT, "tests", "golden", "edge", "in.asym"),
                              api.AlgoParams(est_cov=1, outputfilename="/tmp/raft_b200_nofallback"))
