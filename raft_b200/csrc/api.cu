@@ -822,7 +822,10 @@ extern "C" int raftgpu_ingest_paf(raftgpu_ctx* ctx, const uint8_t* text, size_t 
     }
     if (last_chunk) {
         ctx->paf_done = true;
-        if ((st = start_seq_upload(ctx))) return st; // PAF is on the device: the arena upload can overlap everything that follows
+        // PAF is on the device: the arena upload can overlap everything that follows.  A sharded run starts it after its
+        // exchange instead: the copy engine serves host-to-device copies in order, and the small uploads of the exchange
+        // (bounds, bucket cursors) would otherwise queue behind tens of GB of arena chunks.
+        if (!ctx->shard_begun && (st = start_seq_upload(ctx))) return st;
     }
     cudaEventRecord(ctx->ev[1], ctx->st);
     CK(cudaStreamSynchronize(ctx->st));
@@ -1474,6 +1477,7 @@ static int sharded_finish_impl(raftgpu_ctx* ctx, int ing, raftgpu_stats* out, ra
         CKL();
     }
     cudaEventRecord(ctx->ev[9], ctx->st);
+    if ((st = start_seq_upload(ctx))) return st; // deferred arena upload (no-op otherwise): behind the exchange, beside everything that follows
     // ---- local coverage / repeats / cut points; global numbering and file offsets ride on the synchronisations of these two
     if ((st = raftgpu_finalize(ctx, nullptr))) return st;
     if ((st = layout_outputs(ctx))) return st;

@@ -156,3 +156,25 @@ def test_cli_on_several_gpus(ndev, fastq):
             for suf, data in zip(("coverage.txt", "long_repeats.txt", "long_repeats.bed", "reads.fasta"), (ref.cov_txt, ref.rep_txt, ref.bed_txt, ref.fasta)):
                 assert open(os.path.join(d, f"{tag}.{suf}"), "rb").read() == data, (tag, suf)
         assert outs["one"] == outs["many"]
+
+
+def test_cli_on_two_gpus_simulated_reads():
+    """Simulated-read mode (seqrequester names: genome coordinates in the headers, long_repeats.bed) sharded over two GPUs:
+    the per-rank header tables, the BED slices and their file offsets add up to the single-rank oracle files."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from sim_util import sim_dataset
+    reads, paf = sim_dataset(5)
+    args = ["-e", "30", "-p", "4000", "-l", "8000", "-f", "300", "-v", "200"]
+    ref = O.run(reads, paf, O.make_params(est_cov=30, repeat_length=4000, read_length=8000, flanking_length=300, overlap_length=200))
+    assert ref.status == 0 and ref.real_reads == 0 and len(ref.bed_txt) > 0
+    exe = os.path.join(os.path.dirname(HERE), "raft_b200", "raft")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "r.fa"), "wb").write(synth.format_fasta(reads, wrap=60))
+        open(os.path.join(d, "o.paf"), "wb").write(paf)
+        r = subprocess.run([exe] + args + ["-o", os.path.join(d, "out"), os.path.join(d, "r.fa"), os.path.join(d, "o.paf")],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=dict(os.environ, RAFT_B200_DEVICES="0,1"))
+        assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+        assert "Real Reads 0 " in r.stdout.decode()
+        for suf, data in zip(("coverage.txt", "long_repeats.txt", "long_repeats.bed", "reads.fasta"), (ref.cov_txt, ref.rep_txt, ref.bed_txt, ref.fasta)):
+            assert open(os.path.join(d, f"out.{suf}"), "rb").read() == data, suf
