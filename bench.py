@@ -248,10 +248,7 @@ def emit_all_device(ctx, api, win, win2):
         for off in range(0, n, WINDOW):
             ctx.fetch_async(api.OUT_READS_FASTA, off, win, min(WINDOW, n - off))
 
-    if os.environ.get("RAFT_B200_EMIT_ORDER") == "fasta_first":
-        fasta(); text()
-    else:
-        text(); fasta()
+    text(); fasta()
     ctx.sync()
     return sum(sizes.values())
 

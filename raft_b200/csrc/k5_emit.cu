@@ -27,15 +27,9 @@ namespace raftk {
 // shared buffer laid out at the 16-byte phase of its destination, then aligned 128-bit stores.  No block-level
 // barrier and no per-thread search: the read a slot belongs to is warp-uniform state that only moves when a chunk
 // reaches the end of the current read.
-#ifndef CW_PER_N
-#define CW_PER_N 4
-#endif
-#ifndef CW_MINB
-#define CW_MINB 4
-#endif
 constexpr int CW_WARPS = 8;
 constexpr int CW_THREADS = CW_WARPS * 32;
-constexpr int CW_PER = CW_PER_N;      // slots per lane per chunk
+constexpr int CW_PER = 4;             // slots per lane per chunk (8 doubles the time: the registers spill)
 constexpr int CW_CHUNK = 32 * CW_PER;
 constexpr int CW_BUF = 512 * CW_PER;  // per-warp text buffer
 constexpr int CW_CAP = CW_BUF - 16;   // chunks with more text (tiny reads: many "read i " prefixes) take the direct path
@@ -107,7 +101,7 @@ __device__ __noinline__ int cov_slot_direct(uint8_t* gbase, int x, int wlo, int 
     return x;
 }
 
-__global__ void __launch_bounds__(CW_THREADS, CW_MINB) k_cov_text(CovEmitArgs a, int64_t n_tiles)
+__global__ void __launch_bounds__(CW_THREADS, 4) k_cov_text(CovEmitArgs a, int64_t n_tiles)
 {
     __shared__ __align__(16) uint8_t sbuf[CW_WARPS][CW_BUF];
     __shared__ unsigned s_cov[CT_COV];
@@ -415,13 +409,7 @@ void launch_cov_emit(const CovEmitArgs& a_in, int64_t n_tiles_launch, cudaStream
     CovEmitArgs a = a_in;
     a.text_cap = CW_CAP;
     if (const char* e = getenv("RAFT_B200_COV_CAP")) { int v = atoi(e); if (v >= 0 && v < CW_CAP) a.text_cap = v; } // test knob: force the direct path
-    static int pad = -1; // experiment knob: unused dynamic shared memory that limits how many text CTAs share an SM with the gather
-    if (pad < 0) {
-        const char* e = getenv("RAFT_B200_CW_PAD");
-        pad = e ? atoi(e) : 0;
-        if (pad > 0) cudaFuncSetAttribute(k_cov_text, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    }
-    k_cov_text<<<(unsigned)((n_tiles_launch + CW_WARPS - 1) / CW_WARPS), CW_THREADS, (size_t)pad, st>>>(a, n_tiles_launch);
+    k_cov_text<<<(unsigned)((n_tiles_launch + CW_WARPS - 1) / CW_WARPS), CW_THREADS, 0, st>>>(a, n_tiles_launch);
 }
 
 // ================================================================ K5c long_repeats.txt
@@ -825,9 +813,7 @@ void launch_fasta_emit(const FastaEmitArgs& a, cudaStream_t st)
 {
     if (a.w1 <= a.w0 || a.G <= 0) return;
     int64_t tiles = (a.w1 - 1) / FASTA_TILE - a.w0 / FASTA_TILE + 1;
-    static int per_sm = 0; // experiment knob: gather CTAs per SM (4 fill the register file)
-    if (!per_sm) { const char* e = getenv("RAFT_B200_FE_CTAS"); per_sm = e && atoi(e) > 0 ? atoi(e) : 4; }
-    int64_t grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
+    int64_t grid = tiles < 148 * 4 ? tiles : 148 * 4;
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
         kern<<<(unsigned)grid, FE_THREADS, sizeof(FeSmem), st>>>(a, tiles);

@@ -144,7 +144,12 @@ def test_cli_on_several_gpus(ndev, fastq):
         open(os.path.join(d, "r.fa"), "wb").write(synth.format_fasta(ds.reads, wrap=None if fastq else 70, fastq=fastq))
         half = ds.paf.rfind(b"\n", 0, len(ds.paf) // 2) + 1
         open(os.path.join(d, "a.paf"), "wb").write(ds.paf[:half])
-        open(os.path.join(d, "b.paf"), "wb").write(ds.paf[half:])
+        if fastq:   # the second file gzip-compressed: it cannot be cut into byte ranges and goes to one rank as a whole
+            import gzip
+            with gzip.open(os.path.join(d, "b.paf"), "wb") as f:
+                f.write(ds.paf[half:])
+        else:
+            open(os.path.join(d, "b.paf"), "wb").write(ds.paf[half:])
         outs = {}
         for tag, env in (("one", dict(os.environ, RAFT_B200_MULTI_PAF="1")),
                          ("many", dict(os.environ, RAFT_B200_MULTI_PAF="1", RAFT_B200_DEVICES=",".join(str(k) for k in range(ndev))))):
@@ -178,3 +183,24 @@ def test_cli_on_two_gpus_simulated_reads():
         assert "Real Reads 0 " in r.stdout.decode()
         for suf, data in zip(("coverage.txt", "long_repeats.txt", "long_repeats.bed", "reads.fasta"), (ref.cov_txt, ref.rep_txt, ref.bed_txt, ref.fasta)):
             assert open(os.path.join(d, f"out.{suf}"), "rb").read() == data, suf
+
+
+def test_cli_on_two_gpus_data_error_reaches_every_rank():
+    """A PAF name that is not a read name, in the part of the file one rank reads: that rank reports it, the other one
+    learns about it through the collectives (RAFTGPU_E_PEER) and the process ends with the reference-crash exit code instead
+    of hanging in NCCL."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ds, ref = _oracle_case("C1", 0.2, False, seed=99)
+    lines = ds.paf.split(b"\n")
+    bad = lines[(3 * len(lines)) // 4].split(b"\t")
+    bad[5] = b"not_a_read"
+    lines[(3 * len(lines)) // 4] = b"\t".join(bad)
+    exe = os.path.join(os.path.dirname(HERE), "raft_b200", "raft")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "r.fa"), "wb").write(synth.format_fasta(ds.reads, wrap=80))
+        open(os.path.join(d, "o.paf"), "wb").write(b"\n".join(lines))
+        r = subprocess.run([exe] + ds.args + ["-o", os.path.join(d, "out"), os.path.join(d, "r.fa"), os.path.join(d, "o.paf")],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, env=dict(os.environ, RAFT_B200_DEVICES="0,1"))
+        assert r.returncode == 2, r.stdout.decode() + r.stderr.decode()
+        assert b"not in the reads file" in r.stderr
