@@ -273,31 +273,36 @@ def oracle_digests(reads, paf, args, threads):
             STREAMS[2]: [int(r.bytes[3]), int(r.digest[3])]}, dt, r
 
 
+def write_sample_files_gpu(a, local, scale):
+    """reads.fa + ovl.paf of the config at `scale` in a scratch directory (tmpfs when it fits) -> (dir, fs, fa, pf, meta)"""
+    import torch
+    from raft_b200 import synth_gpu
+    ds = synth_gpu.make_dataset_gpu(a.config, scale, symmetric=not a.asymmetric, device=f"cuda:{local}", with_seq=False)
+    d, fs = scratch_dir(ds.bases * 3.3 + ds.paf.numel() * 2.0)
+    fa, pf = os.path.join(d, "reads.fa"), os.path.join(d, "ovl.paf")
+    chunk = max(1, int(ds.n * (1 << 30) / max(ds.bases, 1)))
+    tbuf = None
+    with open(fa, "wb") as fh:  # ">" name "\n" bases "\n", generated on the device a GiB at a time
+        for r0 in range(0, ds.n, chunk):
+            r1 = min(ds.n, r0 + chunk)
+            tbuf, nb = synth_gpu.gen_fasta_text(ds, r0, r1, tbuf)
+            fh.write(memoryview(tbuf[:nb].cpu().numpy()))
+    with open(pf, "wb") as fh:
+        fh.write(memoryview(ds.paf.cpu().numpy()))
+    meta = (ds.args, ds.n_overlaps, ds.bases, ds.n, int(ds.paf.numel()))
+    del ds, tbuf
+    torch.cuda.empty_cache()
+    return d, fs, fa, pf, meta
+
+
 def file_to_file_leg(a, local, log):
     """raft_b200/raft and the unmodified reference binary on the same files (1/SAMPLE_DIV of the workload); outputs compared byte by byte."""
-    import torch
     from oracle import oracle as O
-    from raft_b200 import synth_gpu
     if not O.have_ref():
         return None
     scale = a.scale / SAMPLE_DIV[a.config]
-    ds = synth_gpu.make_dataset_gpu(a.config, scale, symmetric=not a.asymmetric, device=f"cuda:{local}", with_seq=False)
-    d, fs = scratch_dir(ds.bases * 3.3 + ds.paf.numel() * 2.0)
+    d, fs, fa, pf, (args, n_s, bases, n_reads, paf_bytes) = write_sample_files_gpu(a, local, scale)
     try:
-        fa, pf = os.path.join(d, "reads.fa"), os.path.join(d, "ovl.paf")
-        chunk = max(1, int(ds.n * (1 << 30) / max(ds.bases, 1)))
-        tbuf = None
-        with open(fa, "wb") as fh:  # ">" name "\n" bases "\n", generated on the device a GiB at a time
-            for r0 in range(0, ds.n, chunk):
-                r1 = min(ds.n, r0 + chunk)
-                tbuf, nb = synth_gpu.gen_fasta_text(ds, r0, r1, tbuf)
-                fh.write(memoryview(tbuf[:nb].cpu().numpy()))
-        with open(pf, "wb") as fh:
-            fh.write(memoryview(ds.paf.cpu().numpy()))
-        args, n_s, bases, n_reads = ds.args, ds.n_overlaps, ds.bases, ds.n
-        paf_bytes = int(ds.paf.numel())
-        del ds, tbuf
-        torch.cuda.empty_cache()
         env = dict(os.environ, RAFT_B200_DEVICE=str(local))
         exe = os.path.join(ROOT, "raft_b200", "raft")
         c_own, c_wall, _, _ = run_raft_binary(exe, fa, pf, args, os.path.join(d, "gpu"), env)  # first run: cold page cache, CUDA start-up

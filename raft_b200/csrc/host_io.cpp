@@ -3,7 +3,9 @@
 // through the C ABI in include/raft_b200.h.
 #include <cuda_runtime.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -232,6 +234,72 @@ bool parallel_pwrite(int fd, const uint8_t* src, size_t n, uint64_t at)
     return true;
 }
 
+// threads that fill a mapped output slice: the cores of the box shared out among the ranks, 2..8 each
+int map_threads(int ranks)
+{
+    if (const char* e = getenv("RAFT_B200_IO_THREADS")) return std::max(1, std::min(64, atoi(e)));
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(2, std::min(8, (hw > 0 ? hw : 8) / std::max(ranks, 1)));
+}
+
+// Destination of one rank's slice of an output file: bytes [base, base + total) of a file that will hold `file_total`.
+// The page-cache copy of pwrite runs under the file's inode lock, so several threads writing one file take turns
+// (≈2 GB/s whatever their number); page faults on a shared mapping of the same file do not, so the slice is mapped and
+// filled with memcpy by a few threads.  pwrite stays as the fallback: when the file cannot be mapped, and when the volume is
+// short of space (a fault on a full volume is a SIGBUS, a failed pwrite is an error code the caller can report).
+class SliceWriter {
+public:
+    SliceWriter(int fd, uint64_t base, uint64_t total, uint64_t file_total, int threads) : fd_(fd), threads_(threads)
+    {
+        if (!total || getenv("RAFT_B200_NO_MMAP")) return;
+        struct stat sb;
+        struct statvfs vfs;
+        if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) return;
+        if (fstatvfs(fd, &vfs) != 0 || (uint64_t)vfs.f_bavail * vfs.f_frsize < total + (256ull << 20)) return;
+        {   // grow only: the ranks of a run reach this point in any order
+            static std::mutex           grow;
+            std::lock_guard<std::mutex> g(grow);
+            if (fstat(fd, &sb) != 0) return;
+            if ((uint64_t)sb.st_size < file_total && ftruncate(fd, (off_t)file_total) != 0) return;
+        }
+        const long page = sysconf(_SC_PAGESIZE);
+        lo_ = base & ~(uint64_t)(page - 1);
+        len_ = (size_t)(base + total - lo_);
+        void* m = mmap(nullptr, len_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)lo_);
+        if (m != MAP_FAILED) map_ = (uint8_t*)m;
+    }
+    ~SliceWriter() { if (map_) munmap(map_, len_); }
+    SliceWriter(const SliceWriter&) = delete;
+    SliceWriter& operator=(const SliceWriter&) = delete;
+    bool mapped() const { return map_ != nullptr; }
+    // n bytes at file offset `at` (inside the slice)
+    bool put(const uint8_t* src, size_t n, uint64_t at)
+    {
+        if (!map_) return parallel_pwrite(fd_, src, n, at);
+        uint8_t*     dst = map_ + (at - lo_);
+        const size_t MIN_SLICE = 4u << 20;
+        const int    T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads_, n / MIN_SLICE));
+        if (T == 1) { memcpy(dst, src, n); return true; }
+        // cuts on destination page boundaries, so that no two threads fault the same page
+        const size_t head = (size_t)(-(intptr_t)dst & 4095);
+        const size_t per = (((n - head) + T - 1) / T + 4095) & ~(size_t)4095;
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) {
+            const size_t a = t ? std::min(n, head + per * t) : 0, b = std::min(n, head + per * (t + 1));
+            if (b > a) th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+        }
+        for (auto& x : th) x.join();
+        return true;
+    }
+
+private:
+    int      fd_;
+    int      threads_;
+    uint8_t* map_ = nullptr;
+    uint64_t lo_ = 0;
+    size_t   len_ = 0;
+};
+
 // One piece of input: bytes [off, off+len) of a plain file (len < 0: to the end), or a whole gzip file.
 struct Segment { std::string path; int64_t off = 0, len = -1; bool gz = false; };
 
@@ -395,13 +463,15 @@ extern "C" int raftgpu_load_fasta(const char* path, int64_t* n, int64_t** seq_of
     return RAFTGPU_OK;
 }
 
-// Writes the context's slice of one output stream at `file_base` of the open file: this thread fetches windows into the
-// two pinned buffers (D2H through the C ABI) while a writer thread drains the other buffer with pwrite.
-static bool write_stream(raftgpu_ctx* ctx, int which, int fd, uint64_t file_base, PinnedPair& pp, std::string& err)
+// Writes the context's slice of one output stream at `file_base` of the open file (`file_total` bytes once every rank has
+// written): this thread fetches windows into the two pinned buffers (D2H through the C ABI) while a writer thread drains the
+// other buffer into the file.
+static bool write_stream(raftgpu_ctx* ctx, int which, int fd, uint64_t file_base, uint64_t file_total, int ranks, PinnedPair& pp, std::string& err)
 {
     uint64_t total = 0;
     if (raftgpu_output_size(ctx, which, &total)) { err = raftgpu_last_error(ctx); return false; }
     if (!total) return true;
+    SliceWriter             out(fd, file_base, total, std::max(file_total, file_base + total), map_threads(ranks));
     const size_t            W = pp.cap;
     std::mutex              mu;
     std::condition_variable cv;
@@ -414,7 +484,7 @@ static bool write_stream(raftgpu_ctx* ctx, int which, int fd, uint64_t file_base
             cv.wait(g, [&] { return full[k] || done; });
             if (!full[k]) return;
             g.unlock();
-            if (!werr && !parallel_pwrite(fd, pp.buf[k], len[k], at[k])) werr = true;
+            if (!werr && !out.put(pp.buf[k], len[k], at[k])) werr = true;
             g.lock();
             full[k] = false;
             cv.notify_all();
@@ -583,8 +653,8 @@ extern "C" int raftgpu_break_long_reads_multi(const char* readfilename, int n_pa
     std::string err;
     for (int w = 0; w < 4; w++) {
         const std::string path = pre + OUT_SUFFIX[w];
-        int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        bool ok = fd >= 0 && write_stream(ctx, w, fd, 0, pp, err);
+        int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+        bool ok = fd >= 0 && write_stream(ctx, w, fd, 0, 0, 1, pp, err);
         if (fd >= 0 && ::close(fd) != 0) ok = false;
         if (!ok) { fprintf(stderr, "raft_b200: cannot write %s: %s\n", path.c_str(), err.c_str()); raftgpu_destroy(ctx); return RAFTGPU_E_IO; }
         tm.lap(OUT_SUFFIX[w]);
@@ -720,7 +790,7 @@ extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf
         biggest = std::max(biggest, sz / P + 1);
     }
     for (int w = 0; w < 4; w++) {
-        sh.out_fd[w] = ::open((pre + OUT_SUFFIX[w]).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        sh.out_fd[w] = ::open((pre + OUT_SUFFIX[w]).c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
         if (sh.out_fd[w] < 0) { fprintf(stderr, "raft_b200: cannot open %s%s\n", pre.c_str(), OUT_SUFFIX[w]); destroy_all(); return RAFTGPU_E_IO; }
     }
     tm.lap("contexts + input cuts");
@@ -836,7 +906,7 @@ extern "C" int raftgpu_break_long_reads_mgpu(const char* readfilename, int n_paf
         // ---- outputs: this rank's slice of every file, at its file offset
         std::string err;
         for (int w = 0; w < 4 && rc == RAFTGPU_OK; w++)
-            if (!write_stream(ctx, w, sh.out_fd[w], sh.info[r].stream_base[w], pp, err)) {
+            if (!write_stream(ctx, w, sh.out_fd[w], sh.info[r].stream_base[w], sh.info[r].stream_total[w], P, pp, err)) {
                 std::lock_guard<std::mutex> g(sh.mu);
                 sh.err = err; rc = RAFTGPU_E_IO;
             }
