@@ -15,7 +15,7 @@ $(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/kernels.h $(SRC)/nametable.cuh 
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(OBJ)/host_io.o: $(SRC)/host_io.cpp include/raft_b200.h
+$(OBJ)/host_io.o: $(SRC)/host_io.cpp $(SRC)/file_io.h include/raft_b200.h
 	@mkdir -p $(OBJ)
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
 
